@@ -1,0 +1,272 @@
+// K7/K8: GroupNorm(+SiLU), LayerNorm and row softmax for channels-last activations (HBM-bound kernels).
+//
+// Layout: x[n][pixel][C], C contiguous.  Every thread owns 8 consecutive channels (one 16-byte bf16 vector,
+// two float4 for fp32 input) for all pixels it visits, so the per-channel affine terms live in registers and
+// consecutive threads touch consecutive 16/32-byte pieces of a pixel row (fully coalesced).
+#include "common.cuh"
+#include "internal.h"
+
+namespace rg {
+
+struct GnParams {
+    const void* x1; const void* x2;
+    int C1, C2, C;             // C = C1 + C2
+    int in_f32;
+    int N; long long HW;
+    int groups, cpg; float eps;
+    const float* gamma; const float* beta;
+    float* sums;
+    __nv_bfloat16* y; __nv_bfloat16* raw;
+    int silu;
+    int tpr;                   // threads per pixel row = C / 8
+    int rpb;                   // pixel rows handled concurrently by a block
+    long long pix_per_block;
+};
+
+__device__ __forceinline__ void load8(const GnParams& p, int n, long long pix, int c0, float (&v)[8]) {
+    // c0 is a multiple of 8 and C1 is a multiple of 8, so a vector never straddles the two sources
+    const void* src; int cs, Cs;
+    if (c0 < p.C1) { src = p.x1; cs = c0; Cs = p.C1; } else { src = p.x2; cs = c0 - p.C1; Cs = p.C2; }
+    const long long idx = ((long long)n * p.HW + pix) * Cs + cs;
+    if (p.in_f32) {
+        const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + idx);
+        const float4 a = s[0], b = s[1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src) + idx);
+        float2 f;
+        f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+        f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+        f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+        f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+    }
+}
+
+// grid = (blocks_per_image, N); block = tpr * rpb threads
+__global__ void __launch_bounds__(512) gn_stats_kernel(const GnParams p) {
+    extern __shared__ float s_acc[];          // [groups][2]
+    const int n = blockIdx.y;
+    for (int i = threadIdx.x; i < p.groups * 2; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+    const int tc = threadIdx.x % p.tpr, tr = threadIdx.x / p.tpr;
+    const int c0 = tc * 8;
+    float s[8], ss[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
+    const long long p0 = (long long)blockIdx.x * p.pix_per_block;
+    long long p1 = p0 + p.pix_per_block;
+    if (p1 > p.HW) p1 = p.HW;
+    if (tr < p.rpb) {
+        for (long long pix = p0 + tr; pix < p1; pix += p.rpb) {
+            float v[8];
+            load8(p, n, pix, c0, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s[i] += v[i]; ss[i] += v[i] * v[i]; }
+        }
+        // fold the 8 channels into their (at most two) groups, then one shared atomic per group
+        int g_prev = c0 / p.cpg; float gs = 0.f, gss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int g = (c0 + i) / p.cpg;
+            if (g != g_prev) {
+                atomicAdd(&s_acc[g_prev * 2], gs); atomicAdd(&s_acc[g_prev * 2 + 1], gss);
+                gs = 0.f; gss = 0.f; g_prev = g;
+            }
+            gs += s[i]; gss += ss[i];
+        }
+        atomicAdd(&s_acc[g_prev * 2], gs); atomicAdd(&s_acc[g_prev * 2 + 1], gss);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.groups * 2; i += blockDim.x)
+        atomicAdd(&p.sums[(long long)n * p.groups * 2 + i], s_acc[i]);
+}
+
+__global__ void __launch_bounds__(512) gn_apply_kernel(const GnParams p) {
+    const int n = blockIdx.y;
+    const int tc = threadIdx.x % p.tpr, tr = threadIdx.x / p.tpr;
+    if (tr >= p.rpb) return;
+    const int c0 = tc * 8;
+    float sc[8], sh[8];
+    const float inv_cnt = 1.0f / ((float)p.cpg * (float)p.HW);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i, g = c / p.cpg;
+        const float sum = p.sums[((long long)n * p.groups + g) * 2], sq = p.sums[((long long)n * p.groups + g) * 2 + 1];
+        const float mean = sum * inv_cnt;
+        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + p.eps);
+        sc[i] = rstd * p.gamma[c];
+        sh[i] = p.beta[c] - mean * sc[i];
+    }
+    const long long p0 = (long long)blockIdx.x * p.pix_per_block;
+    long long p1 = p0 + p.pix_per_block;
+    if (p1 > p.HW) p1 = p.HW;
+    for (long long pix = p0 + tr; pix < p1; pix += p.rpb) {
+        float v[8];
+        load8(p, n, pix, c0, v);
+        const long long o = ((long long)n * p.HW + pix) * p.C + c0;
+        if (p.raw) {
+            *reinterpret_cast<uint4*>(p.raw + o) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                               pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float y = v[i] * sc[i] + sh[i];
+            v[i] = p.silu ? silu_f(y) : y;
+        }
+        *reinterpret_cast<uint4*>(p.y + o) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                         pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+}
+
+static int fill_gn(const rg_gn_t* g, GnParams& p, dim3& grid, int& threads) {
+    if (!g || !g->x1 || !g->gamma || !g->beta || !g->sums) return set_error(RG_ERR_ARG, "groupnorm: null pointer");
+    const int C = g->C1 + g->C2;
+    if (g->C1 % 8 || g->C2 % 8 || C % g->groups || g->groups > 64 || C / 8 > 512)
+        return set_error(RG_ERR_ARG, "groupnorm: channels must be multiples of 8 (<= 4096) and divisible by groups");
+    if (g->C2 && !g->x2) return set_error(RG_ERR_ARG, "groupnorm: C2 without x2");
+    p.x1 = g->x1; p.x2 = g->x2; p.C1 = g->C1; p.C2 = g->C2; p.C = C;
+    p.in_f32 = g->in_dtype == RG_DT_F32;
+    p.N = g->N; p.HW = g->HW; p.groups = g->groups; p.cpg = C / g->groups; p.eps = g->eps;
+    p.gamma = g->gamma; p.beta = g->beta; p.sums = g->sums;
+    p.y = reinterpret_cast<__nv_bfloat16*>(g->y); p.raw = reinterpret_cast<__nv_bfloat16*>(g->raw);
+    p.silu = g->silu;
+    p.tpr = C / 8;
+    p.rpb = 256 / p.tpr; if (p.rpb < 1) p.rpb = 1;
+    threads = p.tpr * p.rpb;
+    // aim for ~4 waves of blocks over the chip, at least 8 pixels per row slot
+    long long want_blocks = (4LL * sm_count() + g->N - 1) / g->N;
+    long long ppb = (g->HW + want_blocks - 1) / want_blocks;
+    const long long min_ppb = 8LL * p.rpb;
+    if (ppb < min_ppb) ppb = min_ppb;
+    ppb = (ppb + p.rpb - 1) / p.rpb * p.rpb;
+    p.pix_per_block = ppb;
+    grid = dim3((unsigned)((g->HW + ppb - 1) / ppb), (unsigned)g->N);
+    return RG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm
+// one warp per row; the row lives in registers between the two reduction passes
+template <bool IN_F32>
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ x_, long long rows, int C,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, __nv_bfloat16* __restrict__ y) {
+    constexpr int MAXV = 12;                     // 12 * 32 lanes * 4 = 1536 channels max
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int nv = C >> 2;
+    float4 v[MAXV];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int i = lane + j * 32;
+        if (i < nv) {
+            if (IN_F32) {
+                v[j] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x_) + row * C)[i];
+            } else {
+                const uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x_) + row * C)[i];
+                const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+                v[j] = make_float4(a.x, a.y, b.x, b.y);
+            }
+            sum += v[j].x + v[j].y + v[j].z + v[j].w;
+        }
+    }
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int i = lane + j * 32;
+        if (i < nv) {
+            const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+            sq += a * a + b * b + c * c + d * d;
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int i = lane + j * 32;
+        if (i < nv) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i);
+            const float o0 = (v[j].x - mean) * rstd * g.x + b.x, o1 = (v[j].y - mean) * rstd * g.y + b.y;
+            const float o2 = (v[j].z - mean) * rstd * g.z + b.z, o3 = (v[j].w - mean) * rstd * g.w + b.w;
+            reinterpret_cast<uint2*>(y + row * C)[i] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- row softmax (bf16, in place)
+__global__ void __launch_bounds__(256) softmax_rows_kernel(__nv_bfloat16* x, int cols, long long ld) {
+    __shared__ float red[8];
+    __nv_bfloat16* row = x + (long long)blockIdx.x * ld;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float m = -INFINITY;
+    for (int i = tid; i < cols; i += 256) m = fmaxf(m, __bfloat162float(row[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    __syncthreads();
+    float s = 0.f;
+    for (int i = tid; i < cols; i += 256) s += __expf(__bfloat162float(row[i]) - m);
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i];
+    const float inv = 1.0f / s;
+    for (int i = tid; i < cols; i += 256) row[i] = __float2bfloat16(__expf(__bfloat162float(row[i]) - m) * inv);
+}
+
+}  // namespace rg
+
+using namespace rg;
+
+extern "C" int rg_groupnorm_stats(const rg_gn_t* g, rg_stream_t stream) {
+    GnParams p; dim3 grid; int threads;
+    memset(&p, 0, sizeof(p));
+    int rc = fill_gn(g, p, grid, threads);
+    if (rc) return rc;
+    gn_stats_kernel<<<grid, threads, p.groups * 2 * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    count_launch();
+    return check_launch("gn_stats_kernel");
+}
+
+extern "C" int rg_groupnorm_apply(const rg_gn_t* g, rg_stream_t stream) {
+    GnParams p; dim3 grid; int threads;
+    memset(&p, 0, sizeof(p));
+    int rc = fill_gn(g, p, grid, threads);
+    if (rc) return rc;
+    if (!g->y) return set_error(RG_ERR_ARG, "groupnorm_apply: null output");
+    gn_apply_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    count_launch();
+    return check_launch("gn_apply_kernel");
+}
+
+extern "C" int rg_layernorm(const void* x, int32_t in_dtype, int64_t rows, int32_t C, const float* gamma,
+                            const float* beta, float eps, void* y, rg_stream_t stream) {
+    if (!x || !y || !gamma || !beta) return set_error(RG_ERR_ARG, "layernorm: null pointer");
+    if (C % 4 || C > 1536) return set_error(RG_ERR_ARG, "layernorm: C must be a multiple of 4 and <= 1536");
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (in_dtype == RG_DT_F32)
+        layernorm_kernel<true><<<grid, wpb * 32, 0, s>>>(x, rows, C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y));
+    else
+        layernorm_kernel<false><<<grid, wpb * 32, 0, s>>>(x, rows, C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y));
+    count_launch();
+    return check_launch("layernorm_kernel");
+}
+
+extern "C" int rg_softmax_rows(void* x, int64_t rows, int32_t cols, int64_t ld, rg_stream_t stream) {
+    if (!x) return set_error(RG_ERR_ARG, "softmax_rows: null pointer");
+    softmax_rows_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<__nv_bfloat16*>(x), cols, ld);
+    count_launch();
+    return check_launch("softmax_rows_kernel");
+}

@@ -1,0 +1,288 @@
+"""Tensor-level wrappers over the C ABI (include/restoragen.h).
+
+torch is used for device memory and streams only: every function here enqueues hand-written
+sm_100a kernels from librestoragen.so on torch's current CUDA stream (so the calls can be captured
+by ``torch.cuda.graph``) and returns torch tensors that own the output memory.
+
+Activations are channels-last: ``[N, H, W, C]`` (or ``[rows, C]`` for token matrices).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (RG_ACT_GEGLU, RG_ACT_NONE, RG_ACT_SILU, RG_DT_BF16, RG_DT_F32, RgAct, RgAttn, RgConv, RgGn,
+                   RgSched, check)
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == bf16:
+        return RG_DT_BF16
+    if t.dtype == f32:
+        return RG_DT_F32
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _act_desc(x: torch.Tensor) -> RgAct:
+    assert x.dtype == bf16 and x.dim() == 4 and x.stride(3) == 1, "expect bf16 [N,H,W,C] with contiguous C"
+    N, H, W, Cc = x.shape
+    return RgAct(x.data_ptr(), N, H, W, Cc, x.stride(0), x.stride(1), x.stride(2))
+
+
+def launch_count() -> int:
+    return int(_lib.load().rg_launch_count())
+
+
+def conv2d(x: torch.Tensor, w: torch.Tensor, *, kh: int = 1, kw: int = 1, stride: int = 1, pad_t: int = 0,
+           pad_l: int = 0, OH: int | None = None, OW: int | None = None, x2: torch.Tensor | None = None,
+           bias: torch.Tensor | None = None, bias_n: torch.Tensor | None = None, res: torch.Tensor | None = None,
+           out_bf16: torch.Tensor | bool | None = None, out_f32: torch.Tensor | bool | None = None,
+           act: int = RG_ACT_NONE, scale: float = 1.0, out_strides: tuple | None = None):
+    """Implicit-GEMM convolution / linear (rg_conv2d).  ``x``: bf16 [N,H,W,C]; ``w``: bf16 [Cout, kh*kw*C (+C2)].
+
+    ``out_bf16`` / ``out_f32``: True to allocate a contiguous [N,OH,OW,Cout'] output, or a tensor to write into
+    (with ``out_strides`` = element strides (n, h, w) when it is not contiguous).  Returns (out_bf16, out_f32).
+    """
+    lib = _lib.load()
+    N, H, W, Cin = x.shape
+    OH = H if OH is None else OH
+    OW = W if OW is None else OW
+    Cout = w.shape[0]
+    ktot = kh * kw * Cin + (x2.shape[3] if x2 is not None else 0)
+    assert w.dtype == bf16 and w.is_contiguous() and w.shape[1] == ktot, (w.shape, ktot)
+    Cw = Cout // 2 if act == RG_ACT_GEGLU else Cout
+    if out_bf16 is True:
+        out_bf16 = torch.empty((N, OH, OW, Cw), dtype=bf16, device=x.device)
+    if out_f32 is True:
+        out_f32 = torch.empty((N, OH, OW, Cw), dtype=f32, device=x.device)
+    if out_bf16 is False:
+        out_bf16 = None
+    if out_f32 is False:
+        out_f32 = None
+    if out_strides is None:
+        out_strides = (OH * OW * Cw, OW * Cw, Cw)
+    p = RgConv()
+    p.x = _act_desc(x)
+    p.kh, p.kw, p.stride, p.pad_t, p.pad_l, p.OH, p.OW = kh, kw, stride, pad_t, pad_l, OH, OW
+    if x2 is not None:
+        p.has_x2 = 1
+        p.x2 = _act_desc(x2)
+    p.w, p.Cout = w.data_ptr(), Cout
+    for name, t in (("bias", bias), ("bias_n", bias_n)):
+        if t is not None:
+            assert t.dtype == f32 and t.is_contiguous()
+            setattr(p, name, t.data_ptr())
+    if res is not None:
+        p.res, p.res_dtype = res.data_ptr(), _dt(res)
+    if out_bf16 is not None:
+        assert out_bf16.dtype == bf16
+        p.out_bf16 = out_bf16.data_ptr()
+    if out_f32 is not None:
+        assert out_f32.dtype == f32
+        p.out_f32 = out_f32.data_ptr()
+    p.out_stride_n, p.out_stride_h, p.out_stride_w = out_strides
+    p.act, p.scale = act, scale
+    check(lib.rg_conv2d(C.byref(p), _stream()), "rg_conv2d")
+    return out_bf16, out_f32
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, **kw):
+    """x bf16 [M, K] (row stride arbitrary multiple of 8) -> [M, N]; same epilogue options as conv2d."""
+    M, K = x.shape
+    x4 = x.as_strided((1, 1, M, K), (0, 0, x.stride(0), 1))
+    ob, of = conv2d(x4, w, **kw)
+    return (None if ob is None else ob.view(M, -1)), (None if of is None else of.view(M, -1))
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, out: torch.Tensor | None = None):
+    """q [B,Nq,H,d], k/v [B,Nk,H,d] bf16 views (d contiguous) -> out bf16 [B,Nq,H,d] contiguous."""
+    lib = _lib.load()
+    B, Nq, Hh, d = q.shape
+    Nk = k.shape[1]
+    for t in (q, k, v):
+        assert t.dtype == bf16 and t.stride(3) == 1
+    if out is None:
+        out = torch.empty((B, Nq, Hh, d), dtype=bf16, device=q.device)
+    p = RgAttn()
+    p.q, p.k, p.v, p.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    p.B, p.heads, p.d, p.Nq, p.Nk = B, Hh, d, Nq, Nk
+    p.q_stride_b, p.q_stride_t, p.q_stride_h = q.stride(0), q.stride(1), q.stride(2)
+    p.k_stride_b, p.k_stride_t, p.k_stride_h = k.stride(0), k.stride(1), k.stride(2)
+    p.v_stride_b, p.v_stride_t, p.v_stride_h = v.stride(0), v.stride(1), v.stride(2)
+    p.o_stride_b, p.o_stride_t, p.o_stride_h = out.stride(0), out.stride(1), out.stride(2)
+    p.scale = scale
+    check(lib.rg_attention(C.byref(p), _stream()), "rg_attention")
+    return out
+
+
+def softmax_rows_(x: torch.Tensor):
+    assert x.dtype == bf16 and x.dim() == 2 and x.stride(1) == 1
+    check(_lib.load().rg_softmax_rows(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), _stream()), "rg_softmax_rows")
+    return x
+
+
+def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, groups: int = 32, eps: float = 1e-5,
+              silu: bool = False, x2: torch.Tensor | None = None, want_raw: bool = False,
+              sums: torch.Tensor | None = None):
+    """GroupNorm (+SiLU) over channels-last x1 (optionally concatenated with x2 along C).
+    Returns (y bf16 [N,H,W,C1+C2], raw bf16 copy of the concatenated input or None)."""
+    lib = _lib.load()
+    N, H, W, C1 = x1.shape
+    C2 = 0 if x2 is None else x2.shape[3]
+    assert x1.is_contiguous() and (x2 is None or (x2.is_contiguous() and x2.dtype == x1.dtype))
+    Ct = C1 + C2
+    y = torch.empty((N, H, W, Ct), dtype=bf16, device=x1.device)
+    raw = torch.empty((N, H, W, Ct), dtype=bf16, device=x1.device) if want_raw else None
+    if sums is None:
+        sums = torch.empty((N, groups, 2), dtype=f32, device=x1.device)
+    check(lib.rg_memset_zero(sums.data_ptr(), N * groups * 2 * 4, _stream()), "rg_memset_zero")
+    p = RgGn()
+    p.x1, p.C1, p.x2, p.C2 = x1.data_ptr(), C1, _ptr(x2), C2
+    p.in_dtype, p.N, p.HW, p.groups, p.eps = _dt(x1), N, H * W, groups, eps
+    p.gamma, p.beta, p.sums = gamma.data_ptr(), beta.data_ptr(), sums.data_ptr()
+    p.y, p.raw, p.silu = y.data_ptr(), _ptr(raw), int(silu)
+    check(lib.rg_groupnorm_stats(C.byref(p), _stream()), "rg_groupnorm_stats")
+    check(lib.rg_groupnorm_apply(C.byref(p), _stream()), "rg_groupnorm_apply")
+    return y, raw
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    assert x.is_contiguous() and x.dim() == 2
+    y = torch.empty(x.shape, dtype=bf16, device=x.device)
+    check(_lib.load().rg_layernorm(x.data_ptr(), _dt(x), x.shape[0], x.shape[1], gamma.data_ptr(), beta.data_ptr(),
+                                   eps, y.data_ptr(), _stream()), "rg_layernorm")
+    return y
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    assert t.dtype == f32 and t.dim() == 1
+    if out is None:
+        out = torch.empty((t.shape[0], dim), dtype=bf16, device=t.device)
+    check(_lib.load().rg_timestep_embedding(t.data_ptr(), t.shape[0], dim, out.data_ptr(), _stream()),
+          "rg_timestep_embedding")
+    return out
+
+
+def sched_step(eps_uc: torch.Tensor, sample: torch.Tensor, *, ets: torch.Tensor | None, cur: torch.Tensor | None,
+               do_cfg: bool, guidance: float, store_slot: int, w, use_cur: bool, save_cur: bool,
+               c_sample: float, c_eps: float):
+    p = RgSched()
+    n = sample.numel()
+    assert eps_uc.dtype == f32 and sample.dtype == f32 and eps_uc.numel() == (2 * n if do_cfg else n)
+    p.eps_uc, p.sample, p.ets, p.cur_sample = eps_uc.data_ptr(), sample.data_ptr(), _ptr(ets), _ptr(cur)
+    p.n, p.do_cfg, p.guidance, p.store_slot = n, int(do_cfg), guidance, store_slot
+    for i in range(5):
+        p.w[i] = float(w[i])
+    p.use_cur, p.save_cur, p.c_sample, p.c_eps = int(use_cur), int(save_cur), c_sample, c_eps
+    check(_lib.load().rg_sched_step(C.byref(p), _stream()), "rg_sched_step")
+
+
+def im2col_small(x: torch.Tensor, N_out: int, ksize: int, stride: int, pad: int, OH: int, OW: int,
+                 Kpad: int = 64) -> torch.Tensor:
+    """x f32|bf16 [n_mod,H,W,Cin] -> bf16 [N_out, OH, OW, Kpad] (image n reads x[n % n_mod])."""
+    n_mod, H, W, Cin = x.shape
+    assert x.is_contiguous()
+    out = torch.empty((N_out, OH, OW, Kpad), dtype=bf16, device=x.device)
+    check(_lib.load().rg_im2col_small(x.data_ptr(), _dt(x), N_out, n_mod, H, W, Cin, ksize, stride, pad, OH, OW, Kpad,
+                                      out.data_ptr(), _stream()), "rg_im2col_small")
+    return out
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    N, H, W, Cc = x.shape
+    assert x.dtype == bf16 and x.is_contiguous()
+    y = torch.empty((N, 2 * H, 2 * W, Cc), dtype=bf16, device=x.device)
+    check(_lib.load().rg_upsample2x(x.data_ptr(), N, H, W, Cc, y.data_ptr(), _stream()), "rg_upsample2x")
+    return y
+
+
+def nchw_to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    N, Cc, H, W = x.shape
+    assert x.dtype == f32 and x.is_contiguous()
+    y = torch.empty((N, H, W, Cc), dtype=f32, device=x.device)
+    check(_lib.load().rg_nchw_to_nhwc(x.data_ptr(), N, Cc, H, W, y.data_ptr(), _stream()), "rg_nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
+    N, H, W, Cc = x.shape
+    assert x.dtype == f32 and x.is_contiguous()
+    y = torch.empty((N, Cc, H, W), dtype=f32, device=x.device)
+    check(_lib.load().rg_nhwc_to_nchw(x.data_ptr(), N, Cc, H, W, y.data_ptr(), _stream()), "rg_nhwc_to_nchw")
+    return y
+
+
+def preprocess_u8(img: torch.Tensor, mask: torch.Tensor | None = None) -> torch.Tensor:
+    """u8 [N,H,W,3] -> f32 [N,H,W,3] in [-1,1]; with ``mask`` f32 [N,H,W] also multiplies by (mask < 0.5)."""
+    N, H, W, _ = img.shape
+    assert img.dtype == torch.uint8 and img.is_contiguous()
+    out = torch.empty((N, H, W, 3), dtype=f32, device=img.device)
+    check(_lib.load().rg_preprocess_u8(img.data_ptr(), _ptr(mask), N, H, W, out.data_ptr(), _stream()),
+          "rg_preprocess_u8")
+    return out
+
+
+def postprocess_u8(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    N, H, W, ldc = x.shape
+    assert x.dtype == f32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty((N, H, W, 3), dtype=torch.uint8, device=x.device)
+    check(_lib.load().rg_postprocess_u8(x.data_ptr(), N, H, W, ldc, out.data_ptr(), _stream()), "rg_postprocess_u8")
+    return out
+
+
+def vae_sample(moments: torch.Tensor, eps_post: torch.Tensor, noise: torch.Tensor | None, scaling: float,
+               sqrt_ac: float = 1.0, sqrt_1mac: float = 0.0) -> torch.Tensor:
+    """moments f32 [N,h,w,8]; eps_post/noise f32 [N,h,w,4] -> latents f32 [N,h,w,4]."""
+    N, h, w, ld = moments.shape
+    out = torch.empty((N, h, w, 4), dtype=f32, device=moments.device)
+    check(_lib.load().rg_vae_sample(moments.data_ptr(), ld, eps_post.data_ptr(), _ptr(noise), N * h * w, scaling,
+                                    int(noise is not None), sqrt_ac, sqrt_1mac, out.data_ptr(), _stream()),
+          "rg_vae_sample")
+    return out
+
+
+def pack_unet_input(lat: torch.Tensor, mask: torch.Tensor, masked: torch.Tensor, out: torch.Tensor | None = None):
+    N, h, w, _ = lat.shape
+    if out is None:
+        out = torch.empty((N, h, w, 9), dtype=f32, device=lat.device)
+    check(_lib.load().rg_pack_unet_input(lat.data_ptr(), mask.data_ptr(), masked.data_ptr(), N * h * w,
+                                         out.data_ptr(), _stream()), "rg_pack_unet_input")
+    return out
+
+
+def pointwise_small(x: torch.Tensor, W: torch.Tensor, b: torch.Tensor | None, scale_in: float = 1.0) -> torch.Tensor:
+    """x f32 [..., Cin] -> f32 [..., Cout] with W f32 [Cout, Cin]."""
+    assert x.dtype == f32 and x.is_contiguous() and W.dtype == f32 and W.is_contiguous()
+    Cout, Cin = W.shape
+    out = torch.empty((*x.shape[:-1], Cout), dtype=f32, device=x.device)
+    check(_lib.load().rg_pointwise_small(x.data_ptr(), x.numel() // Cin, Cin, Cout, W.data_ptr(), _ptr(b), scale_in,
+                                         out.data_ptr(), _stream()), "rg_pointwise_small")
+    return out
+
+
+def mask_nearest(mask: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    N, H, W = mask.shape
+    assert mask.dtype == f32 and mask.is_contiguous()
+    out = torch.empty((N, h, w), dtype=f32, device=mask.device)
+    check(_lib.load().rg_mask_nearest(mask.data_ptr(), N, H, W, h, w, out.data_ptr(), _stream()), "rg_mask_nearest")
+    return out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    assert x.dtype == f32 and x.is_contiguous()
+    y = torch.empty(x.shape, dtype=bf16, device=x.device)
+    check(_lib.load().rg_cast_f32_bf16(x.data_ptr(), x.numel(), y.data_ptr(), _stream()), "rg_cast_f32_bf16")
+    return y

@@ -1,0 +1,223 @@
+/*
+ * restoragen.h -- C ABI of librestoragen.so, the B200 (sm_100a) kernel library behind the
+ * RestoraGen Stable-Diffusion sampling loop.
+ *
+ * Boundary.  The reference (qmoututu11/Image_Restoration_and_Enhancement) has no FFI layer of its
+ * own: its hot path is the pair of diffusers pipeline calls made at
+ *     src/inference.py:486-494   (denoise,  StableDiffusionImg2ImgPipeline.__call__)
+ *     src/inference.py:566-573   (sr,       StableDiffusionImg2ImgPipeline.__call__)
+ *     src/inference.py:664-672   (colorize, StableDiffusionImg2ImgPipeline.__call__)
+ *     src/inference.py:758-767   (inpaint,  StableDiffusionInpaintPipeline.__call__)
+ * and everything below those calls is torch -> cuDNN / cuBLASLt / SDPA library kernels.  This header
+ * declares the operator set that replaces that library layer.  The
+ * Python host side (image_restoration_and_enhancement_b200/pipelines.py) re-provides the two pipeline
+ * classes on top of it; INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions.
+ *   - every entry point returns 0 on success, a cudaError_t (> 0) for CUDA failures, or a negative
+ *     RG_ERR_* for argument errors; nothing throws; rg_last_error() returns a message for the
+ *     calling thread;
+ *   - all data pointers are DEVICE pointers; activations are channels-last (N,H,W,C), C contiguous;
+ *   - all work is enqueued on the caller's stream and nothing allocates, so every call can be
+ *     captured into a CUDA graph;
+ *   - bf16 tensors are passed as void*, fp32 as float*.
+ */
+#ifndef RESTORAGEN_H_
+#define RESTORAGEN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rg_stream_t; /* cudaStream_t */
+
+#define RG_OK 0
+#define RG_ERR_ARG (-1)         /* invalid argument / unsupported shape */
+#define RG_ERR_DRIVER (-2)      /* driver entry point (cuTensorMapEncodeTiled) unavailable */
+#define RG_ERR_TENSORMAP (-3)   /* tensor-map encode failed */
+
+#define RG_ACT_NONE 0
+#define RG_ACT_SILU 1
+#define RG_ACT_GEGLU 2          /* columns interleaved a|g per 160-wide tile; output width = Cout/2 */
+
+#define RG_DT_BF16 0
+#define RG_DT_F32 1
+
+const char* rg_last_error(void);
+int rg_version(void);
+/* number of kernel launches issued by this library in the calling process (all threads) */
+int64_t rg_launch_count(void);
+int rg_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1-K4  implicit-GEMM convolution / linear layer on tcgen05 (TMEM accumulators, TMA operand loads).
+ *   replaces nn.Conv2d 3x3 / 1x1 and nn.Linear inside UNet2DConditionModel / AutoencoderKL
+ *   (shapes Appendix C).
+ *
+ *   out[m][co] = act( scale * sum_k A[m][k] * W[co][k] + bias[co] + bias_n[n(m)][co] + res[m][co] )
+ *   where m = (n, oh, ow) and A is the im2col view of x (taps outer, channels inner), optionally
+ *   followed in K by the channels of x2 sampled at the output pixel (a fused 1x1 shortcut).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct rg_act {
+    const void* data;                  /* bf16, element (n=0,h=0,w=0,c=0) */
+    int32_t N, H, W, C;                /* C must be a multiple of 64 */
+    int64_t stride_n, stride_h, stride_w; /* in elements; multiples of 8 */
+} rg_act_t;
+
+typedef struct rg_conv {
+    rg_act_t x;
+    int32_t kh, kw;        /* 1..3 each (2x2 is used by the parity-split upsample convolution) */
+    int32_t stride;        /* 1 or 2 */
+    int32_t pad_t, pad_l;  /* top/left zero padding; bottom/right padding is implied by OH/OW */
+    int32_t OH, OW;
+    int32_t has_x2;
+    rg_act_t x2;           /* same N, spatial dims OH x OW */
+    const void* w;         /* bf16 [Cout][Ktot], Ktot = kh*kw*x.C + x2.C */
+    int32_t Cout;
+    const float* bias;     /* [Cout] or NULL */
+    const float* bias_n;   /* [N][Cout] or NULL */
+    const void* res;       /* residual, same addressing as the outputs, or NULL */
+    int32_t res_dtype;     /* RG_DT_* */
+    void* out_bf16;        /* either or both outputs */
+    float* out_f32;
+    /* address of output pixel (n,oh,ow), in elements, for res and both outputs:
+       n*out_stride_n + oh*out_stride_h + ow*out_stride_w  (strided writes serve the upsample split) */
+    int64_t out_stride_n, out_stride_h, out_stride_w;
+    int32_t act;           /* RG_ACT_* */
+    float scale;
+} rg_conv_t;
+
+int rg_conv2d(const rg_conv_t* p, rg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5/K6  fused flash-style attention on tcgen05: O = softmax(scale * Q K^T) V, no mask.
+ *   replaces F.scaled_dot_product_attention in attn1 (self, N = H*W tokens) and attn2
+ *   (cross, 77 CLIP tokens) of every BasicTransformerBlock.
+ *   q/k/v/out are bf16 [B][tokens][heads][d] views with arbitrary (multiple-of-8) strides.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct rg_attn {
+    const void *q, *k, *v;
+    void* out;
+    int32_t B, heads, d;           /* d in {40, 80, 160} (any multiple of 8 up to 192) */
+    int32_t Nq, Nk;
+    int64_t q_stride_b, q_stride_t, q_stride_h;   /* elements */
+    int64_t k_stride_b, k_stride_t, k_stride_h;
+    int64_t v_stride_b, v_stride_t, v_stride_h;
+    int64_t o_stride_b, o_stride_t, o_stride_h;
+    float scale;
+} rg_attn_t;
+
+int rg_attention(const rg_attn_t* p, rg_stream_t stream);
+
+/* row softmax in place on a bf16 [rows][cols] matrix (VAE mid-block attention, materialised scores) */
+int rg_softmax_rows(void* x, int64_t rows, int32_t cols, int64_t ld, rg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K7  GroupNorm (+SiLU), channels-last.  x may be the channel-concatenation of two tensors
+ *   (skip connections of the up blocks) -- the concat is never materialised in fp32.
+ *   replaces nn.GroupNorm + F.silu.
+ *   rg_groupnorm_stats accumulates (sum, sumsq) per (n, group) into sums[N][G][2] (caller zeroes it);
+ *   rg_groupnorm_apply writes y = silu?((x-mean)*rstd*gamma+beta) as bf16 and optionally the raw
+ *   concatenated input as bf16 (feeds the fused 1x1 shortcut).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct rg_gn {
+    const void* x1; int32_t C1;     /* first source  [N][HW][C1] */
+    const void* x2; int32_t C2;     /* second source [N][HW][C2] or NULL/0 */
+    int32_t in_dtype;               /* RG_DT_* (both sources) */
+    int32_t N; int64_t HW;
+    int32_t groups; float eps;
+    const float* gamma; const float* beta;   /* [C1+C2] */
+    float* sums;                    /* [N][groups][2] fp32 workspace */
+    void* y;                        /* bf16 [N][HW][C1+C2] */
+    void* raw;                      /* bf16 copy of the concatenated input, or NULL */
+    int32_t silu;
+} rg_gn_t;
+
+int rg_groupnorm_stats(const rg_gn_t* p, rg_stream_t stream);
+int rg_groupnorm_apply(const rg_gn_t* p, rg_stream_t stream);
+
+/* K8  LayerNorm over the last dim, affine, eps; x [rows][C] f32|bf16 -> y bf16 */
+int rg_layernorm(const void* x, int32_t in_dtype, int64_t rows, int32_t C, const float* gamma,
+                 const float* beta, float eps, void* y, rg_stream_t stream);
+
+/* K10  sinusoidal timestep embedding (flip_sin_to_cos, freq_shift 0): out bf16 [B][dim] */
+int rg_timestep_embedding(const float* timesteps, int32_t B, int32_t dim, void* out, rg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K11  classifier-free-guidance combine fused with the scheduler update (PLMS or DDIM eta=0).
+ *   replaces `eps = u + g*(c-u)` plus PNDMScheduler.step_plms / DDIMScheduler.step
+ *   (SURVEY.md Appendix A.3a/A.3b).  All state is fp32, layout-agnostic flat arrays of n elements
+ *   per image batch half:  eps_uc holds [2][n] (uncond, cond) when do_cfg else [1][n].
+ *     e      = do_cfg ? u + g*(c-u) : eps
+ *     if store_slot >= 0: ets[store_slot] = e
+ *     e_mix  = sum_i w[i] * (i == 4 ? e : ets[i])            (w[0..3] history slots, w[4] current)
+ *     base   = use_cur ? cur_sample : sample
+ *     if save_cur: cur_sample = sample
+ *     sample_out = c_sample * base - c_eps * e_mix
+ *   The host computes (w, c_sample, c_eps) in the scheduler's own float32 arithmetic.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct rg_sched {
+    const float* eps_uc;
+    float* sample;          /* in/out [n] */
+    float* ets;             /* [4][n] history ring (PLMS) or NULL */
+    float* cur_sample;      /* [n] or NULL */
+    int64_t n;
+    int32_t do_cfg; float guidance;
+    int32_t store_slot;     /* -1: do not store */
+    float w[5];
+    int32_t use_cur, save_cur;
+    float c_sample, c_eps;
+} rg_sched_t;
+
+int rg_sched_step(const rg_sched_t* p, rg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K9/K14  layout / glue kernels
+ * ------------------------------------------------------------------------------------------- */
+/* im2col for convolutions with very few input channels (conv_in of UNet/VAE, post_quant):
+   x f32|bf16 channels-last [n_mod][H][W][Cin] -> bf16 [N*OH*OW][Kpad], K = (tap, c) order, zero padded;
+   output image n reads input image n % n_mod (classifier-free guidance feeds the same latents twice) */
+int rg_im2col_small(const void* x, int32_t in_dtype, int32_t N, int32_t n_mod, int32_t H, int32_t W,
+                    int32_t Cin, int32_t ksize, int32_t stride, int32_t pad, int32_t OH, int32_t OW,
+                    int32_t Kpad, void* out, rg_stream_t stream);
+/* nearest-neighbour 2x upsample, bf16 channels-last */
+int rg_upsample2x(const void* x, int32_t N, int32_t H, int32_t W, int32_t C, void* y, rg_stream_t stream);
+/* f32 NCHW <-> f32 NHWC (latents and RNG draws arrive in torch's NCHW order) */
+int rg_nchw_to_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, float* y, rg_stream_t stream);
+int rg_nhwc_to_nchw(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, float* y, rg_stream_t stream);
+/* VaeImageProcessor.preprocess tail: u8 HWC [N][H][W][3] -> f32 NHWC in [-1,1] (x/255*2-1),
+   optionally multiplied by (mask < 0.5) with mask f32 [N][H][W] (inpaint masked_image) */
+int rg_preprocess_u8(const uint8_t* img, const float* mask, int32_t N, int32_t H, int32_t W, float* out,
+                     rg_stream_t stream);
+/* VaeImageProcessor.postprocess: f32 NHWC [N][H][W][ldc>=3] -> u8 HWC, round(clamp(x/2+.5,0,1)*255) */
+int rg_postprocess_u8(const float* x, int32_t N, int32_t H, int32_t W, int32_t ldc, uint8_t* out,
+                      rg_stream_t stream);
+/* DiagonalGaussianDistribution.sample * scaling fused with scheduler.add_noise:
+   moments f32 NHWC [N][HW][8] (mean 0-3, logvar 4-7), eps_post / noise f32 NHWC [N][HW][4]
+   z = (mean + exp(0.5*clamp(logvar,-30,20))*eps_post) * scaling
+   latents = add_noise ? sqrt_ac*z + sqrt_1mac*noise : z */
+int rg_vae_sample(const float* moments, int64_t moments_ld, const float* eps_post, const float* noise,
+                  int64_t npix, float scaling, int32_t add_noise, float sqrt_ac, float sqrt_1mac,
+                  float* out, rg_stream_t stream);
+/* inpaint UNet input assembly (StableDiffusionInpaintPipeline: cat([latents, mask, masked_image_latents], 1)):
+   f32 [npix][9] <- latents f32 [npix][4], mask f32 [npix], masked latents f32 [npix][4] */
+int rg_pack_unet_input(const float* latents, const float* mask, const float* masked, int64_t npix, float* out,
+                       rg_stream_t stream);
+/* 1x1 convolution with very few channels on fp32 pixels (quant_conv 8->8, post_quant_conv 4->4):
+   out[p][co] = b[co] + sum_c W[co][c] * (x[p][c] * scale_in) */
+int rg_pointwise_small(const float* x, int64_t npix, int32_t Cin, int32_t Cout, const float* W, const float* b,
+                       float scale_in, float* out, rg_stream_t stream);
+/* nearest resize of the binarised mask f32 [N][H][W] -> [N][h][w] (F.interpolate default) */
+int rg_mask_nearest(const float* mask, int32_t N, int32_t H, int32_t W, int32_t h, int32_t w, float* out,
+                    rg_stream_t stream);
+/* elementwise helpers */
+int rg_scale_f32(const float* x, float a, int64_t n, float* y, rg_stream_t stream);
+int rg_cast_f32_bf16(const float* x, int64_t n, void* y, rg_stream_t stream);
+int rg_memset_zero(void* p, int64_t bytes, rg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RESTORAGEN_H_ */

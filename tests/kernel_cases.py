@@ -1,0 +1,323 @@
+"""GPU parity cases for the individual kernels of librestoragen.so.
+
+Each case builds seeded inputs, runs the CUDA kernel through the C ABI (via ops.py) and compares with a plain
+PyTorch fp32 reference of the same op on the same (bf16-rounded) inputs.  The cases are plain functions so they
+can be run one per process by tools/gpu_kernel_check.py (a faulting kernel poisons its CUDA context) and
+in-process by tests/test_kernels_gpu.py.
+
+Tolerances (relative L2 unless noted): bf16 outputs 4e-3 (one bf16 rounding of an fp32-accumulated result is
+2^-9 = 2e-3 worst case), fp32 outputs 2e-5 for GEMMs (fp32 accumulation order differs), attention 8e-3
+(P is rounded to bf16 before the second GEMM, as in every flash-attention kernel).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from image_restoration_and_enhancement_b200 import ops
+from image_restoration_and_enhancement_b200._lib import RG_ACT_GEGLU, RG_ACT_NONE, RG_ACT_SILU
+
+DEV = "cuda"
+TOL_BF16, TOL_F32, TOL_ATTN = 4e-3, 2e-5, 8e-3
+
+
+def _setup():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def pack_w(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, kh, kw] -> [Cout, kh*kw*Cin] (taps outer, channels inner)."""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ GEMM / conv
+def case_linear(M=256, K=128, N=160, bias=True, res=None, act=RG_ACT_NONE, f32_out=False, scale=1.0, seed=0):
+    _setup()
+    x = _rand((M, K), seed)
+    w = _rand((N, K), seed + 1, 1.0 / math.sqrt(K))
+    b = _rand((N,), seed + 2, 0.5, torch.float32) if bias else None
+    r = None
+    if res == "f32":
+        r = _rand((M, N), seed + 3, 1.0, torch.float32)
+    elif res == "bf16":
+        r = _rand((M, N), seed + 3, 1.0)
+    ref = (x.float() @ w.float().t()) * scale
+    if b is not None:
+        ref = ref + b
+    if r is not None:
+        ref = ref + r.float()
+    if act == RG_ACT_SILU:
+        ref = F.silu(ref)
+    ob, of = ops.linear(x, w, bias=b, res=r, act=act, scale=scale, out_bf16=not f32_out, out_f32=f32_out)
+    torch.cuda.synchronize()
+    out = of if f32_out else ob
+    return rel_l2(out, ref), (TOL_F32 if f32_out else TOL_BF16)
+
+
+def case_geglu(M=300, K=320, C4=1280, seed=5):
+    """ff.net.0 (GEGLU): proj -> chunk(2) -> a * gelu(g); weight rows interleaved per 160-wide tile on the host."""
+    _setup()
+    from image_restoration_and_enhancement_b200.weights import interleave_geglu
+    x = _rand((M, K), seed)
+    w = _rand((2 * C4, K), seed + 1, 1.0 / math.sqrt(K))
+    b = _rand((2 * C4,), seed + 2, 0.5, torch.float32)
+    h = x.float() @ w.float().t() + b
+    a, g = h.chunk(2, dim=-1)
+    ref = a * F.gelu(g)
+    wi, bi = interleave_geglu(w, b)
+    ob, _ = ops.linear(x, wi, bias=bi, act=RG_ACT_GEGLU, out_bf16=True)
+    torch.cuda.synchronize()
+    return rel_l2(ob, ref), TOL_BF16
+
+
+def case_conv(N=2, H=16, W=16, Cin=64, Cout=160, k=3, stride=1, pad=1, asym=False, bias=True, bias_n=False,
+              res=None, x2c=0, f32_out=False, seed=10):
+    """3x3 / 1x1 convolution vs F.conv2d.  ``asym``: VAE-encoder downsample (pad (0,1,0,1), stride 2, pad 0)."""
+    _setup()
+    x = _rand((N, H, W, Cin), seed)
+    w = _rand((Cout, Cin, k, k), seed + 1, 1.0 / math.sqrt(Cin * k * k))
+    b = _rand((Cout,), seed + 2, 0.5, torch.float32) if bias else None
+    xn = x.float().permute(0, 3, 1, 2)
+    if asym:
+        ref = F.conv2d(F.pad(xn, (0, 1, 0, 1)), w.float(), None, stride=2, padding=0)
+        pad_t = pad_l = 0
+    else:
+        ref = F.conv2d(xn, w.float(), None, stride=stride, padding=pad)
+        pad_t = pad_l = pad
+    OH, OW = ref.shape[2], ref.shape[3]
+    wp = pack_w(w)
+    x2 = None
+    if x2c:
+        x2 = _rand((N, OH, OW, x2c), seed + 4)
+        w2 = _rand((Cout, x2c), seed + 5, 1.0 / math.sqrt(x2c))
+        ref = ref + torch.einsum("nhwc,oc->nohw", x2.float(), w2.float())
+        wp = torch.cat([wp, w2], dim=1).contiguous()
+    if b is not None:
+        ref = ref + b[None, :, None, None]
+    bn = None
+    if bias_n:
+        bn = _rand((N, Cout), seed + 6, 0.5, torch.float32)
+        ref = ref + bn[:, :, None, None]
+    r = None
+    if res is not None:
+        r = _rand((N, OH, OW, Cout), seed + 3, 1.0, torch.float32 if res == "f32" else torch.bfloat16)
+        ref = ref + r.float().permute(0, 3, 1, 2)
+    ob, of = ops.conv2d(x, wp, kh=k, kw=k, stride=2 if asym else stride, pad_t=pad_t, pad_l=pad_l, OH=OH, OW=OW,
+                        x2=x2, bias=b, bias_n=bn, res=r, out_bf16=not f32_out, out_f32=f32_out)
+    torch.cuda.synchronize()
+    out = (of if f32_out else ob).float().permute(0, 3, 1, 2)
+    return rel_l2(out, ref), (TOL_F32 if f32_out else TOL_BF16)
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def case_attention(B=2, heads=8, d=40, Nq=1024, Nk=None, seed=20, fused_qkv=True):
+    _setup()
+    Nk = Nq if Nk is None else Nk
+    C = heads * d
+    if fused_qkv and Nk == Nq:
+        qkv = _rand((B, Nq, 3 * C), seed)
+        q = qkv[:, :, 0:C].unflatten(2, (heads, d))
+        k = qkv[:, :, C:2 * C].unflatten(2, (heads, d))
+        v = qkv[:, :, 2 * C:].unflatten(2, (heads, d))
+    else:
+        q = _rand((B, Nq, heads, d), seed)
+        kv = _rand((B, Nk, 2 * C), seed + 1)
+        k = kv[:, :, :C].unflatten(2, (heads, d))
+        v = kv[:, :, C:].unflatten(2, (heads, d))
+    scale = d ** -0.5
+    ref = F.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2),
+                                         v.float().transpose(1, 2)).transpose(1, 2)
+    out = ops.attention(q, k, v, scale)
+    torch.cuda.synchronize()
+    return rel_l2(out, ref), TOL_ATTN
+
+
+# ------------------------------------------------------------------------------------------------ norms
+def case_groupnorm(N=2, H=16, W=16, C1=320, C2=0, in_f32=True, silu=True, eps=1e-5, raw=False, seed=30):
+    _setup()
+    dt = torch.float32 if in_f32 else torch.bfloat16
+    x1 = _rand((N, H, W, C1), seed, 1.5, dt) + 0.3
+    x2 = (_rand((N, H, W, C2), seed + 1, 0.7, dt) - 0.2) if C2 else None
+    C = C1 + C2
+    gamma = _rand((C,), seed + 2, 0.2, torch.float32) + 1.0
+    beta = _rand((C,), seed + 3, 0.2, torch.float32)
+    xc = x1 if x2 is None else torch.cat([x1, x2], dim=3)
+    ref = F.group_norm(xc.float().permute(0, 3, 1, 2), 32, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    y, r = ops.groupnorm(x1, gamma, beta, eps=eps, silu=silu, x2=x2, want_raw=raw)
+    torch.cuda.synchronize()
+    err = rel_l2(y.float().permute(0, 3, 1, 2), ref)
+    if raw:
+        err = max(err, rel_l2(r, xc))
+    return err, TOL_BF16
+
+
+def case_layernorm(rows=1000, C=320, in_f32=True, seed=40):
+    _setup()
+    x = _rand((rows, C), seed, 2.0, torch.float32 if in_f32 else torch.bfloat16) + 0.5
+    gamma = _rand((C,), seed + 1, 0.2, torch.float32) + 1.0
+    beta = _rand((C,), seed + 2, 0.2, torch.float32)
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    y = ops.layernorm(x, gamma, beta, 1e-5)
+    torch.cuda.synchronize()
+    return rel_l2(y, ref), TOL_BF16
+
+
+def case_softmax_rows(rows=64, cols=4096, seed=50):
+    _setup()
+    x = _rand((rows, cols), seed, 3.0)
+    ref = torch.softmax(x.float(), dim=-1)
+    ops.softmax_rows_(x)
+    torch.cuda.synchronize()
+    return rel_l2(x, ref), TOL_BF16
+
+
+# ------------------------------------------------------------------------------------------------ glue
+def case_timestep_embedding():
+    _setup()
+    t = torch.tensor([1.0, 501.0, 951.0, 727.0], device=DEV)
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=DEV) / half)
+    a = t[:, None] * freqs[None]
+    ref = torch.cat([torch.cos(a), torch.sin(a)], dim=-1)
+    out = ops.timestep_embedding(t, 320)
+    torch.cuda.synchronize()
+    return float((out.float() - ref).abs().max()), 8e-3     # abs: bf16 rounding of values in [-1,1]
+
+
+def case_sched(do_cfg=True, seed=60):
+    _setup()
+    n = 4 * 64 * 64
+    eps = _rand((2 if do_cfg else 1, n), seed, 1.0, torch.float32)
+    sample = _rand((n,), seed + 1, 1.0, torch.float32)
+    ets = _rand((4, n), seed + 2, 1.0, torch.float32)
+    cur = _rand((n,), seed + 3, 1.0, torch.float32)
+    g = 7.5
+    e = eps[0] + g * (eps[1] - eps[0]) if do_cfg else eps[0]
+    w = [0.0, -59 / 24, 37 / 24, -9 / 24, 55 / 24]      # store into slot 0, history in slots 1..3
+    ref_mix = w[4] * e + w[1] * ets[1] + w[2] * ets[2] + w[3] * ets[3]
+    ref = 1.01 * sample - 0.07 * ref_mix
+    s2, ets2 = sample.clone(), ets.clone()
+    ops.sched_step(eps, s2, ets=ets2, cur=cur, do_cfg=do_cfg, guidance=g, store_slot=0, w=w, use_cur=False,
+                   save_cur=False, c_sample=1.01, c_eps=0.07)
+    torch.cuda.synchronize()
+    err = rel_l2(s2, ref)
+    err = max(err, rel_l2(ets2[0], e))
+    return err, 1e-6
+
+
+def case_im2col(seed=70):
+    _setup()
+    x = _rand((2, 16, 16, 4), seed, 1.0, torch.float32)
+    w = _rand((320, 4, 3, 3), seed + 1, 0.2)
+    ref = F.conv2d(x.to(torch.bfloat16).float().permute(0, 3, 1, 2), w.float(), None, padding=1)
+    cols = ops.im2col_small(x, 4, 3, 1, 1, 16, 16, 64)      # N_out = 4 = 2 x CFG duplication
+    wp = torch.zeros((320, 64), dtype=torch.bfloat16, device=DEV)
+    wp[:, :36] = pack_w(w)
+    ob, _ = ops.conv2d(cols, wp, out_bf16=True)
+    torch.cuda.synchronize()
+    out = ob.float().permute(0, 3, 1, 2)
+    return max(rel_l2(out[:2], ref), rel_l2(out[2:], ref)), TOL_BF16
+
+
+def case_upsample(seed=80):
+    _setup()
+    x = _rand((2, 8, 8, 64), seed)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    y = ops.upsample2x(x)
+    torch.cuda.synchronize()
+    return float((y.float() - ref).abs().max()), 0.0
+
+
+def case_layout_and_io(seed=90):
+    _setup()
+    x = _rand((2, 4, 8, 6), seed, 1.0, torch.float32)
+    y = ops.nchw_to_nhwc(x)
+    z = ops.nhwc_to_nchw(y)
+    e1 = float((y - x.permute(0, 2, 3, 1)).abs().max()) + float((z - x).abs().max())
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randint(0, 256, (2, 16, 16, 3), generator=g, dtype=torch.uint8).to(DEV)
+    pre = ops.preprocess_u8(img)
+    ref = 2.0 * (img.float() / 255.0) - 1.0
+    e2 = float((pre - ref).abs().max())
+    dec = _rand((2, 16, 16, 3), seed + 1, 1.0, torch.float32)
+    post = ops.postprocess_u8(dec)
+    refp = ((dec / 2 + 0.5).clamp(0, 1) * 255).round().to(torch.uint8)
+    e3 = float((post.int() - refp.int()).abs().max())
+    mom = _rand((2, 8, 8, 8), seed + 2, 1.0, torch.float32)
+    ep = _rand((2, 8, 8, 4), seed + 3, 1.0, torch.float32)
+    nz = _rand((2, 8, 8, 4), seed + 4, 1.0, torch.float32)
+    lat = ops.vae_sample(mom, ep, nz, 0.18215, 0.8, 0.6)
+    mean, logvar = mom[..., :4], mom[..., 4:].clamp(-30, 20)
+    refl = 0.8 * ((mean + torch.exp(0.5 * logvar) * ep) * 0.18215) + 0.6 * nz
+    e4 = rel_l2(lat, refl)
+    torch.cuda.synchronize()
+    return max(e1, e2, float(e3), e4 * 1e-0 if e4 > 1e-6 else 0.0), 1e-6
+
+
+CASES = {
+    # --- tcgen05 GEMM, plain linear layers
+    "linear_basic": lambda: case_linear(),
+    "linear_ragged_n320": lambda: case_linear(M=300, K=320, N=320, seed=1),
+    "linear_n128": lambda: case_linear(M=512, K=256, N=128, seed=2),
+    "linear_n64": lambda: case_linear(M=130, K=64, N=64, seed=3),
+    "linear_n4_f32": lambda: case_linear(M=200, K=128, N=4, f32_out=True, seed=4),
+    "linear_n8_bias_f32": lambda: case_linear(M=200, K=512, N=8, f32_out=True, seed=41),
+    "linear_res_f32_silu": lambda: case_linear(M=256, K=192, N=320, res="f32", act=RG_ACT_SILU, seed=5),
+    "linear_res_bf16_f32out": lambda: case_linear(M=256, K=1280, N=640, res="bf16", f32_out=True, seed=6),
+    "linear_scale_nobias": lambda: case_linear(M=4096, K=512, N=4096, bias=False, scale=0.044, seed=7),
+    "linear_tiny_m": lambda: case_linear(M=16, K=1280, N=1280, seed=8),
+    "linear_long_k": lambda: case_linear(M=1024, K=5120, N=1280, seed=9),
+    "geglu": lambda: case_geglu(),
+    # --- implicit-GEMM convolutions
+    "conv3x3_small": lambda: case_conv(),
+    "conv3x3_unet64": lambda: case_conv(N=2, H=64, W=64, Cin=320, Cout=320, bias_n=True, seed=11),
+    "conv3x3_unet8_n3": lambda: case_conv(N=3, H=8, W=8, Cin=1280, Cout=1280, res="f32", f32_out=True, seed=12),
+    "conv3x3_ragged": lambda: case_conv(N=1, H=41, W=62, Cin=128, Cout=128, seed=13),
+    "conv3x3_stride2": lambda: case_conv(N=2, H=32, W=32, Cin=320, Cout=320, stride=2, seed=14),
+    "conv3x3_stride2_odd": lambda: case_conv(N=1, H=41, W=31, Cin=64, Cout=64, stride=2, seed=15),
+    "conv3x3_vae_asym": lambda: case_conv(N=1, H=64, W=64, Cin=128, Cout=128, asym=True, seed=16),
+    "conv3x3_shortcut": lambda: case_conv(N=2, H=16, W=16, Cin=640, Cout=640, x2c=1920, res=None, f32_out=True, seed=17),
+    "conv1x1": lambda: case_conv(N=2, H=32, W=32, Cin=640, Cout=640, k=1, pad=0, res="f32", f32_out=True, seed=18),
+    "conv3x3_vae512_cout3": lambda: case_conv(N=1, H=128, W=128, Cin=128, Cout=3, f32_out=True, seed=19),
+    "conv3x3_wide": lambda: case_conv(N=1, H=8, W=256, Cin=64, Cout=64, seed=20),
+    # --- attention
+    "attn_self_d40": lambda: case_attention(B=2, heads=8, d=40, Nq=1024),
+    "attn_self_d40_4096": lambda: case_attention(B=1, heads=8, d=40, Nq=4096, seed=21),
+    "attn_self_d80": lambda: case_attention(B=2, heads=8, d=80, Nq=1024, seed=22),
+    "attn_self_d160": lambda: case_attention(B=2, heads=8, d=160, Nq=256, seed=23),
+    "attn_self_d160_64": lambda: case_attention(B=3, heads=8, d=160, Nq=64, seed=24),
+    "attn_cross_d40": lambda: case_attention(B=2, heads=8, d=40, Nq=4096, Nk=77, seed=25, fused_qkv=False),
+    "attn_cross_d160": lambda: case_attention(B=2, heads=8, d=160, Nq=64, Nk=77, seed=26, fused_qkv=False),
+    "attn_ragged": lambda: case_attention(B=1, heads=8, d=40, Nq=2542, seed=27),
+    "attn_d64": lambda: case_attention(B=1, heads=4, d=64, Nq=300, seed=28),
+    # --- norms
+    "gn_f32_silu": lambda: case_groupnorm(),
+    "gn_concat_raw": lambda: case_groupnorm(N=2, H=8, W=8, C1=1280, C2=640, raw=True, seed=31),
+    "gn_bf16_nosilu_eps6": lambda: case_groupnorm(N=1, H=64, W=64, C1=128, in_f32=False, silu=False, eps=1e-6, seed=32),
+    "gn_big": lambda: case_groupnorm(N=1, H=256, W=256, C1=128, in_f32=False, seed=33),
+    "ln_f32_320": lambda: case_layernorm(),
+    "ln_bf16_1280": lambda: case_layernorm(rows=333, C=1280, in_f32=False, seed=42),
+    "softmax_rows": lambda: case_softmax_rows(),
+    # --- glue
+    "timestep_embedding": case_timestep_embedding,
+    "sched_cfg": lambda: case_sched(True),
+    "sched_nocfg": lambda: case_sched(False, seed=61),
+    "im2col_conv_in": case_im2col,
+    "upsample2x": case_upsample,
+    "layout_io": case_layout_and_io,
+}
