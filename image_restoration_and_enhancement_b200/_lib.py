@@ -23,8 +23,8 @@ class RgAct(C.Structure):
 class RgConv(C.Structure):
     _fields_ = [("x", RgAct), ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32),
                 ("pad_t", C.c_int32), ("pad_l", C.c_int32), ("OH", C.c_int32), ("OW", C.c_int32),
-                ("has_x2", C.c_int32), ("x2", RgAct), ("w", C.c_void_p), ("Cout", C.c_int32),
-                ("bias", C.c_void_p), ("bias_n", C.c_void_p), ("res", C.c_void_p), ("res_dtype", C.c_int32),
+                ("has_x2", C.c_int32), ("x2", RgAct), ("w", C.c_void_p), ("w_ld", C.c_int64), ("Cout", C.c_int32),
+                ("bias", C.c_void_p), ("bias_n", C.c_void_p), ("bias_n_ld", C.c_int64), ("res", C.c_void_p), ("res_dtype", C.c_int32),
                 ("out_bf16", C.c_void_p), ("out_f32", C.c_void_p),
                 ("out_stride_n", C.c_int64), ("out_stride_h", C.c_int64), ("out_stride_w", C.c_int64),
                 ("act", C.c_int32), ("scale", C.c_float)]

@@ -31,6 +31,7 @@ struct GemmParams {
     int N, OH, OW, Cout;
     const float* bias;
     const float* bias_n;
+    long long bias_n_ld;
     const void* res;
     int res_f32;
     __nv_bfloat16* out_bf16;
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                     tmem_ld_wait();
                     const int col0 = n_tile * BN + c;
                     if (valid && col0 < p.Cout) {
-                        const float* bn_row = p.bias_n ? p.bias_n + (long long)n * p.Cout : nullptr;
+                        const float* bn_row = p.bias_n ? p.bias_n + (long long)n * p.bias_n_ld : nullptr;
                         if (p.vec_ok && col0 + CH <= p.Cout) {
 #pragma unroll
                             for (int g8 = 0; g8 < CH; g8 += 8) {
@@ -331,7 +332,8 @@ using namespace rg;
 extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (!c || !c->x.data || !c->w) return set_error(RG_ERR_ARG, "rg_conv2d: null pointer");
-    if (c->x.C % 64 != 0 || (c->has_x2 && c->x2.C % 64 != 0))
+    const bool plain = c->kh == 1 && c->kw == 1 && !c->has_x2;      // single K segment: a ragged last K block is
+    if (!plain && (c->x.C % 64 != 0 || (c->has_x2 && c->x2.C % 64 != 0)))   // zero-filled by TMA in both operands
         return set_error(RG_ERR_ARG, "rg_conv2d: channel counts must be multiples of 64");
     if (c->kh < 1 || c->kh > 3 || c->kw < 1 || c->kw > 3 || (c->stride != 1 && c->stride != 2))
         return set_error(RG_ERR_ARG, "rg_conv2d: unsupported kernel size / stride");
@@ -356,7 +358,7 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
     gp.n_tiles_m = gp.tiles_w * gp.tiles_h * gp.tiles_n;
     gp.N = N; gp.OH = OH; gp.OW = OW; gp.Cout = c->Cout;
 
-    const int cblk = c->x.C / 64;
+    const int cblk = (c->x.C + 63) / 64;
     int n_items = 0, n_maps = 0, rc;
     const char* xb = reinterpret_cast<const char*>(c->x.data);
     if (c->stride == 1) {
@@ -399,7 +401,7 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
     }
     for (int i = n_maps; i < 5; ++i) gp.amap[i] = gp.amap[0];
     gp.n_items = n_items;
-    gp.total_kblk = ktot / 64;
+    gp.total_kblk = (ktot + 63) / 64;
 
     // tile width in N
     int BN;
@@ -416,7 +418,9 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
 
     {
         cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)c->Cout};
-        cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+        const long long w_ld = c->w_ld ? c->w_ld : ktot;
+        if (w_ld % 8 || w_ld < ktot) return set_error(RG_ERR_ARG, "rg_conv2d: w_ld must be a multiple of 8 and >= Ktot");
+        cuuint64_t strides[1] = {(cuuint64_t)w_ld * 2};
         cuuint32_t box[2] = {64, (cuuint32_t)BN};
         cuuint32_t estr[2] = {1, 1};
         if (reinterpret_cast<uintptr_t>(c->w) & 15) return set_error(RG_ERR_ARG, "rg_conv2d: weights must be 16-B aligned");
@@ -425,7 +429,7 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
         if (rc) return rc;
     }
 
-    gp.bias = c->bias; gp.bias_n = c->bias_n;
+    gp.bias = c->bias; gp.bias_n = c->bias_n; gp.bias_n_ld = c->bias_n_ld;
     gp.res = c->res; gp.res_f32 = c->res_dtype == RG_DT_F32;
     gp.out_bf16 = reinterpret_cast<__nv_bfloat16*>(c->out_bf16);
     gp.out_f32 = c->out_f32;
@@ -434,7 +438,7 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
     const bool aligned = (c->out_stride_n % 8 == 0) && (c->out_stride_h % 8 == 0) && (c->out_stride_w % 8 == 0) &&
                          !(reinterpret_cast<uintptr_t>(c->out_bf16) & 15) && !(reinterpret_cast<uintptr_t>(c->out_f32) & 15) &&
                          !(reinterpret_cast<uintptr_t>(c->res) & 15) && !(reinterpret_cast<uintptr_t>(c->bias) & 15) &&
-                         !(reinterpret_cast<uintptr_t>(c->bias_n) & 15) && (c->Cout % 4 == 0);
+                         !(reinterpret_cast<uintptr_t>(c->bias_n) & 15) && (c->bias_n_ld % 4 == 0) && (c->Cout % 4 == 0);
     gp.vec_ok = aligned ? 1 : 0;
     if (c->act == RG_ACT_GEGLU && !aligned) return set_error(RG_ERR_ARG, "rg_conv2d: GEGLU output must be 16-B aligned");
 

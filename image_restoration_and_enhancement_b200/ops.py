@@ -38,7 +38,10 @@ def _dt(t: torch.Tensor) -> int:
 def _act_desc(x: torch.Tensor) -> RgAct:
     assert x.dtype == bf16 and x.dim() == 4 and x.stride(3) == 1, "expect bf16 [N,H,W,C] with contiguous C"
     N, H, W, Cc = x.shape
-    return RgAct(x.data_ptr(), N, H, W, Cc, x.stride(0), x.stride(1), x.stride(2))
+    sw = x.stride(2) if W > 1 else max(x.stride(2), (Cc + 7) // 8 * 8)
+    sh = x.stride(1) if H > 1 else max(x.stride(1), sw * W)       # size-1 dims: any sane non-zero pitch
+    sn = x.stride(0) if N > 1 else max(x.stride(0), sh * H)
+    return RgAct(x.data_ptr(), N, H, W, Cc, sn, sh, sw)
 
 
 def launch_count() -> int:
@@ -49,7 +52,7 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, *, kh: int = 1, kw: int = 1, stride
            pad_l: int = 0, OH: int | None = None, OW: int | None = None, x2: torch.Tensor | None = None,
            bias: torch.Tensor | None = None, bias_n: torch.Tensor | None = None, res: torch.Tensor | None = None,
            out_bf16: torch.Tensor | bool | None = None, out_f32: torch.Tensor | bool | None = None,
-           act: int = RG_ACT_NONE, scale: float = 1.0, out_strides: tuple | None = None):
+           act: int = RG_ACT_NONE, scale: float = 1.0, out_strides: tuple | None = None, w_ld: int = 0):
     """Implicit-GEMM convolution / linear (rg_conv2d).  ``x``: bf16 [N,H,W,C]; ``w``: bf16 [Cout, kh*kw*C (+C2)].
 
     ``out_bf16`` / ``out_f32``: True to allocate a contiguous [N,OH,OW,Cout'] output, or a tensor to write into
@@ -61,7 +64,9 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, *, kh: int = 1, kw: int = 1, stride
     OW = W if OW is None else OW
     Cout = w.shape[0]
     ktot = kh * kw * Cin + (x2.shape[3] if x2 is not None else 0)
-    assert w.dtype == bf16 and w.is_contiguous() and w.shape[1] == ktot, (w.shape, ktot)
+    assert w.dtype == bf16 and w.stride(1) == 1 and w.shape[1] == ktot, (w.shape, ktot)
+    if w_ld == 0 and w.stride(0) != ktot:
+        w_ld = w.stride(0)
     Cw = Cout // 2 if act == RG_ACT_GEGLU else Cout
     if out_bf16 is True:
         out_bf16 = torch.empty((N, OH, OW, Cw), dtype=bf16, device=x.device)
@@ -79,11 +84,13 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, *, kh: int = 1, kw: int = 1, stride
     if x2 is not None:
         p.has_x2 = 1
         p.x2 = _act_desc(x2)
-    p.w, p.Cout = w.data_ptr(), Cout
-    for name, t in (("bias", bias), ("bias_n", bias_n)):
-        if t is not None:
-            assert t.dtype == f32 and t.is_contiguous()
-            setattr(p, name, t.data_ptr())
+    p.w, p.w_ld, p.Cout = w.data_ptr(), w_ld, Cout
+    if bias is not None:
+        assert bias.dtype == f32 and bias.is_contiguous() and bias.numel() == Cout
+        p.bias = bias.data_ptr()
+    if bias_n is not None:
+        assert bias_n.dtype == f32 and bias_n.dim() == 2 and bias_n.stride(1) == 1 and bias_n.shape == (N, Cout)
+        p.bias_n, p.bias_n_ld = bias_n.data_ptr(), bias_n.stride(0)
     if res is not None:
         p.res, p.res_dtype = res.data_ptr(), _dt(res)
     if out_bf16 is not None:

@@ -62,7 +62,7 @@ int rg_device_sm_count(void);
  * ------------------------------------------------------------------------------------------- */
 typedef struct rg_act {
     const void* data;                  /* bf16, element (n=0,h=0,w=0,c=0) */
-    int32_t N, H, W, C;                /* C must be a multiple of 64 */
+    int32_t N, H, W, C;                /* C: multiple of 64 (any size for a plain 1x1 / linear layer) */
     int64_t stride_n, stride_h, stride_w; /* in elements; multiples of 8 */
 } rg_act_t;
 
@@ -75,9 +75,11 @@ typedef struct rg_conv {
     int32_t has_x2;
     rg_act_t x2;           /* same N, spatial dims OH x OW */
     const void* w;         /* bf16 [Cout][Ktot], Ktot = kh*kw*x.C + x2.C */
+    int64_t w_ld;          /* row pitch of w in elements (0 = Ktot); multiple of 8 */
     int32_t Cout;
     const float* bias;     /* [Cout] or NULL */
-    const float* bias_n;   /* [N][Cout] or NULL */
+    const float* bias_n;   /* per-image bias [N][bias_n_ld] (time-embedding projection) or NULL */
+    int64_t bias_n_ld;     /* row pitch of bias_n in elements (multiple of 4) */
     const void* res;       /* residual, same addressing as the outputs, or NULL */
     int32_t res_dtype;     /* RG_DT_* */
     void* out_bf16;        /* either or both outputs */
