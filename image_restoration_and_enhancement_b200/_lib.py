@@ -70,7 +70,7 @@ SIGNATURES = {
     "rg_timestep_embedding": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "rg_sched_step": (C.c_int, [C.POINTER(RgSched), _p]),
     "rg_im2col_small": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p]),
-    "rg_upsample2x": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
+    "rg_upsample_nearest": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p]),
     "rg_nchw_to_nhwc": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "rg_nhwc_to_nchw": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "rg_preprocess_u8": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),

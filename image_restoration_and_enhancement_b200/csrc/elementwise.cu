@@ -80,13 +80,16 @@ __global__ void im2col_small_kernel(const void* x_, int N, int n_mod, int H, int
 }
 
 // ---------------------------------------------------------------------------------------------- nearest 2x upsample (bf16, 16-B vectors)
-__global__ void upsample2x_kernel(const uint4* x, int N, int H, int W, int C8, uint4* y) {
-    const long long total = (long long)N * (2 * H) * (2 * W) * C8;
+// F.interpolate(mode="nearest"): src = min(floor(dst * in / out), in - 1)
+__global__ void upsample_nearest_kernel(const uint4* x, int N, int H, int W, int C8, int OH, int OW, uint4* y) {
+    const long long total = (long long)N * OH * OW * C8;
+    const float sh = (float)H / (float)OH, sw = (float)W / (float)OW;
     RG_GRID_STRIDE(i, total) {
         const int c = (int)(i % C8); long long r = i / C8;
-        const int ow = (int)(r % (2 * W)); r /= (2 * W);
-        const int oh = (int)(r % (2 * H)); const int n = (int)(r / (2 * H));
-        y[i] = x[(((long long)n * H + (oh >> 1)) * W + (ow >> 1)) * C8 + c];
+        const int ow = (int)(r % OW); r /= OW;
+        const int oh = (int)(r % OH); const int n = (int)(r / OH);
+        const int ih = min((int)floorf(oh * sh), H - 1), iw = min((int)floorf(ow * sw), W - 1);
+        y[i] = x[(((long long)n * H + ih) * W + iw) * C8 + c];
     }
 }
 
@@ -227,13 +230,14 @@ extern "C" int rg_im2col_small(const void* x, int32_t in_dtype, int32_t N, int32
     return check_launch("im2col_small_kernel");
 }
 
-extern "C" int rg_upsample2x(const void* x, int32_t N, int32_t H, int32_t W, int32_t C, void* y, rg_stream_t stream) {
-    if (!x || !y || C % 8) return set_error(RG_ERR_ARG, "upsample2x: bad argument");
-    const long long total = (long long)N * 4 * H * W * (C / 8);
-    upsample2x_kernel<<<grid_for(total, 256), 256, 0, RG_STREAM(stream)>>>(reinterpret_cast<const uint4*>(x), N, H, W,
-                                                                            C / 8, reinterpret_cast<uint4*>(y));
+extern "C" int rg_upsample_nearest(const void* x, int32_t N, int32_t H, int32_t W, int32_t C, int32_t OH, int32_t OW,
+                                   void* y, rg_stream_t stream) {
+    if (!x || !y || C % 8 || OH < 1 || OW < 1) return set_error(RG_ERR_ARG, "upsample_nearest: bad argument");
+    const long long total = (long long)N * OH * OW * (C / 8);
+    upsample_nearest_kernel<<<grid_for(total, 256), 256, 0, RG_STREAM(stream)>>>(
+        reinterpret_cast<const uint4*>(x), N, H, W, C / 8, OH, OW, reinterpret_cast<uint4*>(y));
     count_launch();
-    return check_launch("upsample2x_kernel");
+    return check_launch("upsample_nearest_kernel");
 }
 
 extern "C" int rg_nchw_to_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, float* y, rg_stream_t stream) {

@@ -1,0 +1,167 @@
+"""Per-image restoration metrics and their bookkeeping (reference ``/root/reference/src/metrics.py``).
+
+``MetricsCalculator.calculate_psnr/ssim`` restate the two scikit-image calls the reference makes
+(``src/metrics.py:87`` ``psnr(gt, pred, data_range=255.0)``; ``:95`` ``ssim(gt, pred, data_range=255.0,
+channel_axis=2)``) -- scikit-image itself is not installed here -- in float64 numpy/scipy, and ``aggregate``
+is the reference's statistics block (``:338-346``).  ``gather_per_image`` is the multi-GPU piece: every rank
+contributes its per-image float64 values with their global indices, rank 0 reorders by index and aggregates, so
+the result is bit-identical to a single-process run (partial sums are never all-reduced).
+LPIPS needs pretrained AlexNet + linear heads that are not available offline: ``use_lpips`` is accepted for API
+parity and yields ``None`` values unless a callable is supplied.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Callable
+
+import numpy as np
+
+
+def load_image(path: Path) -> np.ndarray:
+    """RGB uint8 array, decoded the way the reference does (cv2.imread + BGR2RGB, ``src/metrics.py:40-46``)."""
+    import cv2
+    img = cv2.imread(str(path))
+    if img is None:
+        raise ValueError(f"Could not load image: {path}")
+    return cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+
+
+def _match_shape(pred: np.ndarray, gt: np.ndarray) -> np.ndarray:
+    if pred.shape != gt.shape:
+        import cv2
+        pred = cv2.resize(pred, (gt.shape[1], gt.shape[0]))
+    return pred
+
+
+def psnr(gt: np.ndarray, pred: np.ndarray, data_range: float = 255.0) -> float:
+    """skimage.metrics.peak_signal_noise_ratio: float64 MSE, 10 log10(R^2 / mse)."""
+    a, b = gt.astype(np.float64), pred.astype(np.float64)
+    err = np.mean((a - b) ** 2, dtype=np.float64)
+    with np.errstate(divide="ignore"):
+        return float(10 * np.log10((data_range ** 2) / err))
+
+
+def _ssim_2d(im1: np.ndarray, im2: np.ndarray, data_range: float, win_size: int = 7, K1: float = 0.01,
+             K2: float = 0.03) -> float:
+    from scipy.ndimage import uniform_filter
+    im1, im2 = im1.astype(np.float64), im2.astype(np.float64)
+    NP = win_size ** 2
+    cov_norm = NP / (NP - 1)                         # sample covariance
+    ux, uy = uniform_filter(im1, size=win_size), uniform_filter(im2, size=win_size)
+    uxx, uyy, uxy = (uniform_filter(im1 * im1, size=win_size), uniform_filter(im2 * im2, size=win_size),
+                     uniform_filter(im1 * im2, size=win_size))
+    vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+    C1, C2 = (K1 * data_range) ** 2, (K2 * data_range) ** 2
+    A1, A2, B1, B2 = 2 * ux * uy + C1, 2 * vxy + C2, ux ** 2 + uy ** 2 + C1, vx + vy + C2
+    S = (A1 * A2) / (B1 * B2)
+    pad = (win_size - 1) // 2
+    return float(S[pad:-pad, pad:-pad].mean(dtype=np.float64))
+
+
+def ssim(gt: np.ndarray, pred: np.ndarray, data_range: float = 255.0, channel_axis: int | None = 2) -> float:
+    """skimage.metrics.structural_similarity (7x7 uniform window, per-channel mean of the cropped SSIM map)."""
+    if channel_axis is None or gt.ndim == 2:
+        return _ssim_2d(gt, pred, data_range)
+    vals = np.empty(gt.shape[channel_axis], dtype=np.float64)
+    for c in range(gt.shape[channel_axis]):
+        vals[c] = _ssim_2d(np.take(gt, c, axis=channel_axis), np.take(pred, c, axis=channel_axis), data_range)
+    return float(vals.mean())
+
+
+class MetricsCalculator:
+    def __init__(self, use_lpips: bool = True, use_fid: bool = False, device: str = "cpu",
+                 lpips_fn: Callable[[np.ndarray, np.ndarray], float] | None = None):
+        self.lpips_fn = lpips_fn
+        self.use_lpips = use_lpips and lpips_fn is not None
+        self.use_fid = False              # FID needs Inception weights that are not available offline
+        self.device = device
+
+    def calculate_psnr(self, pred: np.ndarray, gt: np.ndarray) -> float:
+        return psnr(gt, _match_shape(pred, gt), data_range=255.0)
+
+    def calculate_ssim(self, pred: np.ndarray, gt: np.ndarray) -> float:
+        return ssim(gt, _match_shape(pred, gt), data_range=255.0, channel_axis=2 if gt.ndim == 3 else None)
+
+    def calculate_lpips(self, pred: np.ndarray, gt: np.ndarray):
+        if not self.use_lpips:
+            return None
+        return float(self.lpips_fn(_match_shape(pred, gt), gt))
+
+    def calculate_all(self, pred: np.ndarray, gt: np.ndarray) -> dict:
+        out = {"psnr": self.calculate_psnr(pred, gt), "ssim": self.calculate_ssim(pred, gt)}
+        if self.use_lpips:
+            out["lpips"] = self.calculate_lpips(pred, gt)
+        return out
+
+
+def aggregate(values: list[float]) -> dict:
+    """mean / std (ddof 0) / min / max / median in float64, as ``src/metrics.py:338-346``."""
+    return {"mean": np.mean(values), "std": np.std(values), "min": np.min(values), "max": np.max(values),
+            "median": np.median(values)}
+
+
+def summarize(task: str, per_image: dict[str, list[float]], num_samples: int) -> dict:
+    return {"task": task, "num_samples": num_samples,
+            "metrics": {k: aggregate(v) for k, v in per_image.items() if v}}
+
+
+def gather_per_image(indices: list[int], metrics: dict[str, list[float]], group=None) -> dict[str, list[float]] | None:
+    """All ranks pass the global indices of the images they evaluated and the per-image values; rank 0 gets the
+    values of every image in global-index order (others get None).  Works on NCCL (device tensors) and gloo."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        order = np.argsort(np.asarray(indices, dtype=np.int64), kind="stable")
+        return {k: [v[i] for i in order] for k, v in metrics.items()}
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    keys = sorted(metrics)
+    n_local = torch.tensor([len(indices)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    n_max = int(max(int(c) for c in counts))
+    # one float64 row per image: [global index, metric values...]; exact for indices < 2^53
+    rows = torch.full((n_max, 1 + len(keys)), float("nan"), dtype=torch.float64, device=dev)
+    if indices:
+        local = np.column_stack([np.asarray(indices, dtype=np.float64)] + [np.asarray(metrics[k], dtype=np.float64) for k in keys])
+        rows[:len(indices)] = torch.from_numpy(local).to(dev)
+    gathered = [torch.empty_like(rows) for _ in range(world)]
+    dist.all_gather(gathered, rows, group=group)
+    if rank != 0:
+        return None
+    allrows = np.concatenate([g[:int(c)].cpu().numpy() for g, c in zip(gathered, counts)], axis=0)
+    order = np.argsort(allrows[:, 0].astype(np.int64), kind="stable")
+    allrows = allrows[order]
+    return {k: [float(x) for x in allrows[:, 1 + j]] for j, k in enumerate(keys)}
+
+
+def evaluate_task(pred_dir: Path, gt_dir: Path, task_name: str = "denoise", use_lpips: bool = True,
+                  use_fid: bool = False, device: str = "cpu") -> dict:
+    """Directory-based evaluation with the reference's file matching (``src/metrics.py:238-348``)."""
+    calc = MetricsCalculator(use_lpips=use_lpips, use_fid=use_fid, device=device)
+    exts = {".jpg", ".jpeg", ".png"}
+    pred_files = sorted(f for f in Path(pred_dir).iterdir() if f.suffix.lower() in exts)
+    pairs = []
+    for pf in pred_files:
+        gf = Path(gt_dir) / pf.name
+        if not gf.exists():
+            for ext in (".jpg", ".jpeg", ".png"):
+                alt = Path(gt_dir) / (pf.stem + ext)
+                if alt.exists():
+                    gf = alt
+                    break
+        if gf.exists():
+            pairs.append((pf, gf))
+    if not pairs:
+        raise ValueError(f"No matching files found between {pred_dir} and {gt_dir}")
+    per_image: dict[str, list[float]] = {"psnr": [], "ssim": []}
+    for pf, gf in pairs:
+        try:
+            m = calc.calculate_all(load_image(pf), load_image(gf))
+        except Exception as e:             # the reference skips unreadable pairs
+            print(f"Error processing {pf.name}: {e}")
+            continue
+        for k, v in m.items():
+            if v is not None:
+                per_image.setdefault(k, []).append(v)
+    return summarize(task_name, per_image, len(pairs))

@@ -18,6 +18,25 @@ from ._lib import (RG_ACT_GEGLU, RG_ACT_NONE, RG_ACT_SILU, RG_DT_BF16, RG_DT_F32
 
 bf16, f32 = torch.bfloat16, torch.float32
 
+# When set to a list, conv2d / attention append (start_event, end_event, algorithmic_flops, kind) per launch
+# (bench.py's roofline leg); None in normal operation.
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _prof_end(e0, flops, kind):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        PROFILE.append((e0, e1, flops, kind))
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -101,7 +120,9 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, *, kh: int = 1, kw: int = 1, stride
         p.out_f32 = out_f32.data_ptr()
     p.out_stride_n, p.out_stride_h, p.out_stride_w = out_strides
     p.act, p.scale = act, scale
+    e0 = _prof_begin()
     check(lib.rg_conv2d(C.byref(p), _stream()), "rg_conv2d")
+    _prof_end(e0, 2.0 * N * OH * OW * Cout * ktot, "gemm")
     return out_bf16, out_f32
 
 
@@ -130,7 +151,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, o
     p.v_stride_b, p.v_stride_t, p.v_stride_h = v.stride(0), v.stride(1), v.stride(2)
     p.o_stride_b, p.o_stride_t, p.o_stride_h = out.stride(0), out.stride(1), out.stride(2)
     p.scale = scale
+    e0 = _prof_begin()
     check(lib.rg_attention(C.byref(p), _stream()), "rg_attention")
+    _prof_end(e0, 4.0 * B * Hh * Nq * Nk * d, "attention")
     return out
 
 
@@ -207,11 +230,12 @@ def im2col_small(x: torch.Tensor, N_out: int, ksize: int, stride: int, pad: int,
     return out
 
 
-def upsample2x(x: torch.Tensor) -> torch.Tensor:
+def upsample_nearest(x: torch.Tensor, OH: int, OW: int) -> torch.Tensor:
     N, H, W, Cc = x.shape
     assert x.dtype == bf16 and x.is_contiguous()
-    y = torch.empty((N, 2 * H, 2 * W, Cc), dtype=bf16, device=x.device)
-    check(_lib.load().rg_upsample2x(x.data_ptr(), N, H, W, Cc, y.data_ptr(), _stream()), "rg_upsample2x")
+    y = torch.empty((N, OH, OW, Cc), dtype=bf16, device=x.device)
+    check(_lib.load().rg_upsample_nearest(x.data_ptr(), N, H, W, Cc, OH, OW, y.data_ptr(), _stream()),
+          "rg_upsample_nearest")
     return y
 
 
@@ -251,10 +275,11 @@ def postprocess_u8(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Te
 
 
 def vae_sample(moments: torch.Tensor, eps_post: torch.Tensor, noise: torch.Tensor | None, scaling: float,
-               sqrt_ac: float = 1.0, sqrt_1mac: float = 0.0) -> torch.Tensor:
+               sqrt_ac: float = 1.0, sqrt_1mac: float = 0.0, out: torch.Tensor | None = None) -> torch.Tensor:
     """moments f32 [N,h,w,8]; eps_post/noise f32 [N,h,w,4] -> latents f32 [N,h,w,4]."""
     N, h, w, ld = moments.shape
-    out = torch.empty((N, h, w, 4), dtype=f32, device=moments.device)
+    if out is None:
+        out = torch.empty((N, h, w, 4), dtype=f32, device=moments.device)
     check(_lib.load().rg_vae_sample(moments.data_ptr(), ld, eps_post.data_ptr(), _ptr(noise), N * h * w, scaling,
                                     int(noise is not None), sqrt_ac, sqrt_1mac, out.data_ptr(), _stream()),
           "rg_vae_sample")

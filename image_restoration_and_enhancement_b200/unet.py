@@ -65,6 +65,7 @@ class _Transformer:
         self.w_ff, self.b_ff = g(t + "ff.net.2.weight").to(dev, bf16).contiguous(), f(t + "ff.net.2.bias")
         self.C = self.w_in.shape[0]
         self.kv = None            # cross-attention K/V of the current prompt batch: bf16 [Bu, 77, 2C]
+        self.kv_bufs = {}         # persistent per batch size, so captured graphs keep valid addresses
 
 
 class UNetB200:
@@ -122,10 +123,8 @@ class UNetB200:
             if i < 3:
                 w = sd[f"up_blocks.{i}.upsamplers.0.conv.weight"]
                 bias = f(f"up_blocks.{i}.upsamplers.0.conv.bias")
-                if split_upsample:
-                    blk["up"] = ([(py, px, wp.to(dev, bf16)) for py, px, wp in upsample_parity_weights(w)], bias)
-                else:
-                    blk["up"] = (pack_conv(w).to(dev, bf16), bias)
+                blk["up"] = ([(py, px, wp.to(dev, bf16)) for py, px, wp in upsample_parity_weights(w)],
+                             pack_conv(w).to(dev, bf16), bias)
             self.up.append(blk)
         self.w_temb = torch.cat(temb_w, dim=0).to(dev, bf16).contiguous()
         self.b_temb = torch.cat(temb_b, dim=0).to(dev, f32).contiguous()
@@ -141,8 +140,11 @@ class UNetB200:
         c = ctx.to(self.device)
         c = (ops.cast_bf16(c.to(f32).contiguous()) if c.dtype != bf16 else c.contiguous()).view(Bu * T, D)
         for t in self.transformers:
-            kv, _ = ops.linear(c, t.w_kv2, out_bf16=True)
-            t.kv = kv.view(Bu, T, 2 * t.C)
+            buf = t.kv_bufs.get((Bu, T))
+            if buf is None:
+                buf = t.kv_bufs[(Bu, T)] = torch.empty((Bu, T, 2 * t.C), dtype=bf16, device=self.device)
+            ops.linear(c, t.w_kv2, out_bf16=buf.view(1, 1, Bu * T, 2 * t.C))
+            t.kv = buf
         self.ctx_batch = Bu
 
     # ------------------------------------------------------------------------------------------ blocks
@@ -187,12 +189,13 @@ class UNetB200:
         ob, of = ops.conv2d(tb.view(N, H, W, Cc), t.w_out, bias=t.b_out, res=x, out_f32=True, out_bf16=want_bf16)
         return of, ob
 
-    def _upsample_conv(self, up, xb):
+    def _upsample_conv(self, up, xb, OH, OW):
         N, H, W, Cc = xb.shape
-        wts, bias = up
-        if not self.split_upsample:
-            u = ops.upsample2x(xb)
-            _, of = ops.conv2d(u, wts, kh=3, kw=3, pad_t=1, pad_l=1, bias=bias, out_f32=True)
+        wts, w_plain, bias = up
+        if not self.split_upsample or (OH, OW) != (2 * H, 2 * W):
+            # diffusers passes the skip's size to F.interpolate when the input is not divisible by 8
+            u = ops.upsample_nearest(xb, OH, OW)
+            _, of = ops.conv2d(u, w_plain, kh=3, kw=3, pad_t=1, pad_l=1, bias=bias, out_f32=True)
             return of
         out = torch.empty((N, 2 * H, 2 * W, Cc), dtype=f32, device=xb.device)
         sn, sh, sw = out.stride(0), out.stride(1), out.stride(2)
@@ -243,7 +246,11 @@ class UNetB200:
                 if has_attn:
                     x, xb = self._transformer(blk["attn"][j], x, want_bf16=last)
             if blk["up"] is not None:
-                x = self._upsample_conv(blk["up"], xb)
+                if h % 8 or w % 8:                # forward_upsample_size: target = next skip's spatial size
+                    OH, OW = skips[-1].shape[1], skips[-1].shape[2]
+                else:
+                    OH, OW = 2 * x.shape[1], 2 * x.shape[2]
+                x = self._upsample_conv(blk["up"], xb, OH, OW)
         y, _ = ops.groupnorm(x, self.g_out, self.b_out, eps=1e-5, silu=True)
         _, eps = ops.conv2d(y, self.w_conv_out, kh=3, kw=3, pad_t=1, pad_l=1, bias=self.b_conv_out, out_f32=True)
         return eps

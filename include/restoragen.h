@@ -184,8 +184,11 @@ int rg_sched_step(const rg_sched_t* p, rg_stream_t stream);
 int rg_im2col_small(const void* x, int32_t in_dtype, int32_t N, int32_t n_mod, int32_t H, int32_t W,
                     int32_t Cin, int32_t ksize, int32_t stride, int32_t pad, int32_t OH, int32_t OW,
                     int32_t Kpad, void* out, rg_stream_t stream);
-/* nearest-neighbour 2x upsample, bf16 channels-last */
-int rg_upsample2x(const void* x, int32_t N, int32_t H, int32_t W, int32_t C, void* y, rg_stream_t stream);
+/* nearest-neighbour resize (F.interpolate mode="nearest"), bf16 channels-last [N][H][W][C] -> [N][OH][OW][C];
+   only used when an upsampler's target is not exactly 2x (UNet inputs not divisible by 8) -- the exact-2x case is
+   folded into the convolution as four parity convolutions */
+int rg_upsample_nearest(const void* x, int32_t N, int32_t H, int32_t W, int32_t C, int32_t OH, int32_t OW,
+                        void* y, rg_stream_t stream);
 /* f32 NCHW <-> f32 NHWC (latents and RNG draws arrive in torch's NCHW order) */
 int rg_nchw_to_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, float* y, rg_stream_t stream);
 int rg_nhwc_to_nchw(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, float* y, rg_stream_t stream);

@@ -194,8 +194,13 @@ class Upsample2D(nn.Module):
         super().__init__()
         self.conv = nn.Conv2d(ch, ch, 3, padding=1)
 
-    def forward(self, x):
-        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+    def forward(self, x, output_size=None):
+        # diffusers: explicit `size=` when the UNet input is not divisible by 2**num_upsamplers
+        if output_size is None:
+            x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+        else:
+            x = F.interpolate(x, size=output_size, mode="nearest")
+        return self.conv(x)
 
 
 class DownBlock(nn.Module):
@@ -250,14 +255,15 @@ class UpBlock(nn.Module):
                 self.attentions.append(Transformer2DModel(heads, out_ch // heads, out_ch, cross_dim, groups))
         self.upsamplers = nn.ModuleList([Upsample2D(out_ch)]) if add_up else None
 
-    def forward(self, x, skips, temb, context):
+    def forward(self, x, skips, temb, context, forward_upsample_size=False):
         for i, r in enumerate(self.resnets):
             x = torch.cat([x, skips.pop()], dim=1)
             x = r(x, temb)
             if self.attentions is not None:
                 x = self.attentions[i](x, context)
         if self.upsamplers is not None:
-            x = self.upsamplers[0](x)
+            size = tuple(skips[-1].shape[2:]) if forward_upsample_size else None
+            x = self.upsamplers[0](x, size)
         return x
 
 
@@ -304,7 +310,9 @@ class UNet2DConditionModel(nn.Module):
             x, outs = blk(x, temb, encoder_hidden_states)
             skips.extend(outs)
         x = self.mid_block(x, temb, encoder_hidden_states)
+        # default_overall_up_factor = 2 ** 3: inputs not divisible by 8 make every upsampler use the skip's size
+        fus = any(d % 8 != 0 for d in sample.shape[-2:])
         for blk in self.up_blocks:
-            x = blk(x, skips, temb, encoder_hidden_states)
+            x = blk(x, skips, temb, encoder_hidden_states, fus)
         x = F.silu(self.conv_norm_out(x))
         return self.conv_out(x)

@@ -236,11 +236,14 @@ def case_im2col(seed=70):
 
 def case_upsample(seed=80):
     _setup()
-    x = _rand((2, 8, 8, 64), seed)
-    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
-    y = ops.upsample2x(x)
-    torch.cuda.synchronize()
-    return float((y.float() - ref).abs().max()), 0.0
+    x = _rand((2, 6, 8, 64), seed)
+    errs = []
+    for size in ((12, 16), (11, 16), (11, 15)):
+        ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=size, mode="nearest").permute(0, 2, 3, 1)
+        y = ops.upsample_nearest(x, *size)
+        torch.cuda.synchronize()
+        errs.append(float((y.float() - ref).abs().max()))
+    return max(errs), 0.0
 
 
 def case_layout_and_io(seed=90):
@@ -318,6 +321,6 @@ CASES = {
     "sched_cfg": lambda: case_sched(True),
     "sched_nocfg": lambda: case_sched(False, seed=61),
     "im2col_conv_in": case_im2col,
-    "upsample2x": case_upsample,
+    "upsample_nearest": case_upsample,
     "layout_io": case_layout_and_io,
 }

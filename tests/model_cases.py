@@ -1,0 +1,245 @@
+"""Model-level parity cases: the CUDA path (through the C ABI) against the fp32 oracle restatement on the same
+seeded inputs and the same random-init weights (weights.random_state_dict: bf16-representable values, so the only
+difference is arithmetic).  Gates from BASELINE.json's north_star: per-step UNet rel-L2 <= 1e-2, final image
+PSNR >= 40 dB."""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+import torch
+
+from image_restoration_and_enhancement_b200 import ops
+from image_restoration_and_enhancement_b200.pipelines import (StableDiffusionImg2ImgPipeline,
+                                                               StableDiffusionInpaintPipeline)
+from image_restoration_and_enhancement_b200.unet import UNetB200
+from image_restoration_and_enhancement_b200.vae import VAEB200
+from image_restoration_and_enhancement_b200.weights import random_state_dict, unet_param_shapes, vae_param_shapes
+
+DEV = "cuda"
+UNET_TOL = 1e-2
+PSNR_MIN = 40.0
+
+
+def _setup():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+def psnr_u8(a: np.ndarray, b: np.ndarray) -> float:
+    mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+    return float("inf") if mse == 0 else 10 * math.log10(255.0 ** 2 / mse)
+
+
+_cache: dict = {}
+
+
+def oracle_unet(in_channels=4, seed=0):
+    key = ("ounet", in_channels, seed)
+    if key not in _cache:
+        from oracle.unet import UNet2DConditionModel, UNetConfig
+        sd = random_state_dict(unet_param_shapes(in_channels=in_channels), seed)
+        m = UNet2DConditionModel(UNetConfig(in_channels=in_channels))
+        m.load_state_dict(sd, strict=True)
+        _cache[key] = (m.to(DEV).eval(), sd)
+    return _cache[key]
+
+
+def oracle_vae(seed=1):
+    key = ("ovae", seed)
+    if key not in _cache:
+        from oracle.vae import AutoencoderKL
+        sd = random_state_dict(vae_param_shapes(), seed)
+        m = AutoencoderKL()
+        m.load_state_dict(sd, strict=True)
+        _cache[key] = (m.to(DEV).eval(), sd)
+    return _cache[key]
+
+
+def synth_image(seed: int, H: int = 512, W: int = 512) -> np.ndarray:
+    """Smooth seeded test image (low-pass random field + gradient), uint8 HWC."""
+    rng = np.random.default_rng(seed)
+    low = rng.standard_normal((H // 32 + 2, W // 32 + 2, 3))
+    t = torch.from_numpy(low).permute(2, 0, 1)[None].float()
+    up = torch.nn.functional.interpolate(t, size=(H, W), mode="bicubic", align_corners=False)[0].permute(1, 2, 0).numpy()
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = 127 + 50 * up + 30 * np.sin(xx / 37.0)[..., None] + 20 * (yy / H)[..., None]
+    return np.ascontiguousarray(np.clip(img, 0, 255).astype(np.uint8))
+
+
+# ------------------------------------------------------------------------------------------------ UNet
+@torch.no_grad()
+def case_unet(in_channels=4, B=1, h=64, w=64, cfg=True, t=501.0, seed=0):
+    _setup()
+    om, sd = oracle_unet(in_channels, seed)
+    key = ("unet", in_channels, seed)
+    if key not in _cache:
+        _cache[key] = UNetB200(sd, in_channels=in_channels, device=DEV)
+    um = _cache[key]
+    g = torch.Generator().manual_seed(100 + seed)
+    Bu = 2 * B if cfg else B
+    lat = torch.randn((B, in_channels, h, w), generator=g).to(DEV)
+    ctx = torch.randn((Bu, 77, 768), generator=g).to(DEV)
+    x_ref = torch.cat([lat] * 2) if cfg else lat
+    ref = om(x_ref, torch.tensor(t, device=DEV), ctx)                       # [Bu,4,h,w]
+    um.prepare_context(ctx)
+    ts = torch.full((Bu,), t, dtype=torch.float32, device=DEV)
+    eps = um.forward(ops.nchw_to_nhwc(lat.contiguous()), ts)
+    torch.cuda.synchronize()
+    out = ops.nhwc_to_nchw(eps)
+    return rel_l2(out, ref), UNET_TOL
+
+
+# ------------------------------------------------------------------------------------------------ VAE
+@torch.no_grad()
+def case_vae_encode(B=1, H=512, W=512, seed=1):
+    _setup()
+    om, sd = oracle_vae(seed)
+    if ("vae", seed) not in _cache:
+        _cache[("vae", seed)] = VAEB200(sd, device=DEV)
+    vm = _cache[("vae", seed)]
+    img = np.stack([synth_image(7 + i, H, W) for i in range(B)])
+    x = ops.preprocess_u8(torch.from_numpy(img).to(DEV))
+    ref = om.quant_conv(om.encoder(x.permute(0, 3, 1, 2).contiguous()))     # [B,8,h,w]
+    mom = vm.encode_moments(x)
+    torch.cuda.synchronize()
+    return rel_l2(mom.permute(0, 3, 1, 2), ref), 1.5e-2
+
+
+@torch.no_grad()
+def case_vae_decode(B=1, h=64, w=64, seed=1):
+    _setup()
+    om, sd = oracle_vae(seed)
+    if ("vae", seed) not in _cache:
+        _cache[("vae", seed)] = VAEB200(sd, device=DEV)
+    vm = _cache[("vae", seed)]
+    g = torch.Generator().manual_seed(55)
+    z = (torch.randn((B, 4, h, w), generator=g) * 0.18215).to(DEV)
+    ref = om.decode(z / 0.18215)
+    img = vm.decode(ops.nchw_to_nhwc(z.contiguous()))
+    torch.cuda.synchronize()
+    ref_u8 = ((ref / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1) * 255).round().to(torch.uint8).cpu().numpy()
+    out_u8 = ops.postprocess_u8(img).cpu().numpy()
+    p = psnr_u8(out_u8, ref_u8)
+    return rel_l2(img.permute(0, 3, 1, 2), ref), 2e-2, p
+
+
+# ------------------------------------------------------------------------------------------------ whole pipeline
+@torch.no_grad()
+def case_pipeline(task="denoise", H=512, W=512, B=1, seed=0, graph=True):
+    """Full sampling run vs the oracle pipeline: per-step guided-eps rel-L2 (each step fed the CUDA path's own
+    UNet input, so the figure isolates one UNet evaluation) and PSNR of the final uint8 image."""
+    _setup()
+    from oracle.pipelines import OraclePipeline, Trace
+    params = {"denoise": dict(steps=20, strength=0.5, g=5.0, kind="pndm", cin=4),
+              "colorize": dict(steps=30, strength=0.75, g=7.5, kind="pndm", cin=4),
+              "sr": dict(steps=20, strength=0.8, g=0.0, kind="pndm", cin=4),
+              "inpaint": dict(steps=30, strength=0.6, g=5.0, kind="ddim", cin=9)}[task]
+    cin = params["cin"]
+    ou, usd = oracle_unet(cin, seed)
+    ov, vsd = oracle_vae(seed + 1)
+    cls = StableDiffusionInpaintPipeline if cin == 9 else StableDiffusionImg2ImgPipeline
+    key = ("pipe", task if cin == 9 else "img2img", seed)
+    if key not in _cache:
+        from image_restoration_and_enhancement_b200.pipelines import _Tokenizer, make_text_encoder
+        from image_restoration_and_enhancement_b200.schedulers import SCHEDULERS
+        sched = SCHEDULERS["DDIMScheduler" if cin == 9 else "PNDMScheduler"]()
+        _cache[key] = cls(dict(usd), dict(vsd), sched, make_text_encoder(seed + 2), _Tokenizer(None)).to(DEV)
+    pipe = _cache[key]
+    pipe.use_cuda_graph = graph
+    g = torch.Generator().manual_seed(200 + seed)
+    pe = torch.randn((1, 77, 768), generator=g).to(DEV)
+    ne = torch.randn((1, 77, 768), generator=g).to(DEV)
+    img = np.stack([synth_image(11 + i, H, W) for i in range(B)])
+    gens = [torch.Generator(device=DEV).manual_seed(42) for _ in range(B)]
+    trace: dict = {}
+    kw = dict(prompt_embeds=pe, negative_prompt_embeds=ne, strength=params["strength"],
+              num_inference_steps=params["steps"], guidance_scale=params["g"], generator=gens,
+              output_type="np_u8", trace=trace)
+    mask = None
+    if cin == 9:
+        mask = np.zeros((B, H, W), dtype=np.uint8)
+        mask[:, H // 4:H // 2, W // 3:2 * W // 3] = 255
+        out = pipe(image=img, mask_image=mask, **kw).images
+    else:
+        out = pipe(image=img, **kw).images
+    torch.cuda.synchronize()
+
+    # ---- oracle run on the same inputs and draws (B independent generators seeded 42 => identical draws per image)
+    op = OraclePipeline(ou, ov, params["kind"])
+    x = (torch.from_numpy(img).to(DEV).float() / 255.0).permute(0, 3, 1, 2) * 2.0 - 1.0
+    otrace = Trace()
+    refs = []
+    for i in range(B):
+        gi = torch.Generator(device=DEV).manual_seed(42)
+        if cin == 9:
+            m = (torch.from_numpy(mask[i:i + 1]).to(DEV).float() / 255.0 >= 0.5).float()[:, None]
+            refs.append(op.inpaint(x[i:i + 1], m, pe, ne, strength=params["strength"],
+                                   num_inference_steps=params["steps"], guidance_scale=params["g"], generator=gi,
+                                   trace=otrace if i == 0 else None))
+        else:
+            refs.append(op.img2img(x[i:i + 1], pe, ne, strength=params["strength"],
+                                   num_inference_steps=params["steps"], guidance_scale=params["g"], generator=gi,
+                                   trace=otrace if i == 0 else None))
+    ref = np.concatenate(refs)
+    res = {"psnr": psnr_u8(out, ref), "steps": len(trace["timesteps"]), "timesteps_match": trace["timesteps"] == otrace.timesteps}
+    res["init_latents_rel"] = rel_l2(ops.nhwc_to_nchw(trace["init_latents"])[0:1], otrace.init_latents)
+    res["final_latents_rel"] = rel_l2(ops.nhwc_to_nchw(trace["final_latents"])[0:1], otrace.final_latents)
+    # per-step UNet error with the CUDA path's own inputs replayed through the oracle UNet
+    do_cfg = params["g"] > 1.0
+    Bu = 2 * B if do_cfg else B
+    embeds = torch.cat([ne.repeat(B, 1, 1), pe.repeat(B, 1, 1)]) if do_cfg else pe.repeat(B, 1, 1)
+    step_err = []
+    for i in (0, len(trace["timesteps"]) // 2, len(trace["timesteps"]) - 1):
+        xin = ops.nhwc_to_nchw(trace["unet_in"][i].contiguous())
+        xin = torch.cat([xin] * 2) if do_cfg else xin
+        ref_eps = ou(xin, torch.tensor(float(trace["timesteps"][i]), device=DEV), embeds)
+        got = ops.nhwc_to_nchw(trace["eps_uc"][i].contiguous())
+        step_err.append(rel_l2(got, ref_eps))
+    res["unet_step_rel"] = step_err
+    return res
+
+
+# ------------------------------------------------------------------------------------------------ timing helper
+@torch.no_grad()
+def time_unet(B=8, cfg=True, h=64, w=64, iters=5, graph=True, in_channels=4):
+    _setup()
+    sd = random_state_dict(unet_param_shapes(in_channels=in_channels), 0)
+    um = UNetB200(sd, in_channels=in_channels, device=DEV)
+    Bu = 2 * B if cfg else B
+    lat = torch.randn((B, h, w, in_channels), device=DEV)
+    ctx = torch.randn((Bu, 77, 768), device=DEV)
+    um.prepare_context(ctx)
+    ts = torch.full((Bu,), 500.0, device=DEV)
+    n0 = ops.launch_count()
+    um.forward(lat, ts)
+    launches = ops.launch_count() - n0
+    torch.cuda.synchronize()
+    if graph:
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            um.forward(lat, ts)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            um.forward(lat, ts)
+        fn = gr.replay
+    else:
+        fn = lambda: um.forward(lat, ts)
+    for _ in range(2):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 0.8033e12 * Bu * (h * w) / 4096.0
+    return {"B": B, "Bu": Bu, "ms": ms, "tflops": flops / ms / 1e9, "launches": launches, "graph": graph}
