@@ -23,6 +23,19 @@ struct AttnParams {
     float scale_log2;     // scale * log2(e)
 };
 
+constexpr int TMEM_COLS_FOR(int dv) { return dv <= 128 ? 256 : 512; }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float y;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+    return y;
+}
+
 template <int DKA, int DV, int BKV>
 struct AttnCfg {
     static constexpr int Q_BYTES = DKA * 128 * 128;
@@ -31,25 +44,30 @@ struct AttnCfg {
     static constexpr int V_BYTES = DKA * KV_ATOM_BYTES;
     static constexpr int P_BYTES = (BKV / 64) * 128 * 128;
     static constexpr int STAGES = 2;
-    static constexpr int SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + P_BYTES + 1024;
-    static constexpr int TMEM_COLS = DV <= 128 ? 256 : 512;
+    static constexpr int TILE_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + P_BYTES;
+    // barriers live behind the tiles; there is no static shared memory, so the dynamic window starts 1024-aligned
+    // (checked at run time) and no alignment slack is needed: d=40 uses 112.1 KB and two CTAs share an SM
+    static constexpr int SMEM_BYTES = TILE_BYTES + 128;
+    static constexpr int MIN_CTAS = (2 * (SMEM_BYTES + 1024) <= 228 * 1024 && TMEM_COLS_FOR(DV) <= 256) ? 2 : 1;
+    static constexpr int TMEM_COLS = TMEM_COLS_FOR(DV);
     static constexpr int O_COL = 128;
 };
 
 constexpr int kAttnThreads = 192;
 
 template <int DKA, int DV, int BKV>
-__global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(kAttnThreads, AttnCfg<DKA, DV, BKV>::MIN_CTAS)
+attention_kernel(const __grid_constant__ AttnParams p) {
     using Cfg = AttnCfg<DKA, DV, BKV>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(16) uint8_t smem[];                    // window-relative base 0: no static smem
+    if ((smem_u32(smem) & 1023u) != 0) __trap();                       // SWIZZLE_128B tiles need 1024-B alignment
     uint8_t* sQ = smem;
     uint8_t* sKV = sQ + Cfg::Q_BYTES;                                  // [stage][K | V]
     uint8_t* sP = sKV + Cfg::STAGES * (Cfg::K_BYTES + Cfg::V_BYTES);
-
-    __shared__ __align__(8) uint64_t q_full, s_full, p_full, o_full;
-    __shared__ __align__(8) uint64_t kv_full[Cfg::STAGES], kv_empty[Cfg::STAGES];
-    __shared__ uint32_t tmem_base_smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::TILE_BYTES);
+    uint64_t& q_full = bars[0]; uint64_t& s_full = bars[1]; uint64_t& p_full = bars[2]; uint64_t& o_full = bars[3];
+    uint64_t* kv_full = bars + 4; uint64_t* kv_empty = bars + 6;
+    uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -137,6 +155,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __grid_co
             mbar_wait(&s_full, j & 1);
             tc_fence_after();
             const int kv_left = p.Nk - j * BKV;              // columns >= kv_left are padding
+            const bool full = kv_left >= BKV;                // warp-uniform: only the last tile can be ragged
             // ---- pass 1: row max of the raw logits
             float mx = -INFINITY;
 #pragma unroll 1
@@ -144,12 +163,17 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __grid_co
                 uint32_t v[32];
                 tmem_ld32(s_tmem + c, v);
                 tmem_ld_wait();
+                if (full) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c + i < kv_left) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c + i < kv_left) mx = fmaxf(mx, __uint_as_float(v[i]));
+                }
             }
             const float m_new = fmaxf(m_run, mx * p.scale_log2);
-            const float alpha = exp2f(m_run - m_new);
+            const float alpha = ex2_approx(m_run - m_new);
             // ---- pass 2: p = 2^(s*scale*log2e - m), row sum, bf16 P -> swizzled smem
             float l_tile = 0.f;
 #pragma unroll 1
@@ -158,11 +182,19 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __grid_co
                 tmem_ld32(s_tmem + c, v);
                 tmem_ld_wait();
                 float pv[32];
+                if (full) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float e = exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_new);
-                    pv[i] = (c + i < kv_left) ? e : 0.f;
-                    l_tile += pv[i];
+                    for (int i = 0; i < 32; ++i) {
+                        pv[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
+                        l_tile += pv[i];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float e = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
+                        pv[i] = (c + i < kv_left) ? e : 0.f;
+                        l_tile += pv[i];
+                    }
                 }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {

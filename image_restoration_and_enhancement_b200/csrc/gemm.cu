@@ -7,9 +7,10 @@
 //   hardware, which is exactly the convolution's zero padding.  Stride-2 convolutions read four "parity"
 //   views of the input (one tensor map each), so they are plain shifted boxes as well.
 // * B is the packed weight matrix [Cout][taps*Cin (+C2)], K-major.
-// * Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..5 =
-//   epilogue (TMEM -> registers -> global).  The accumulator is double-buffered in TMEM so the epilogue
-//   of tile i overlaps the main loop of tile i+1.
+// * Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..9 =
+//   epilogue (TMEM -> registers -> global; two warps per TMEM lane quarter, each draining half of the tile's
+//   columns).  The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of
+//   tile i+1.
 // * Epilogue fuses: scale, bias, per-image bias (time embedding), residual add (bf16 or fp32), SiLU,
 //   GEGLU (a * gelu(g)), and writes bf16 and/or fp32, with arbitrary output pixel strides.
 #include "common.cuh"
@@ -55,7 +56,7 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
 };
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
 __device__ __forceinline__ float apply_act(float x, int act) { return act == 1 ? silu_f(x) : x; }
 
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full_bar[s], 1); mbar_init(&acc_empty_bar[s], 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full_bar[s], 1); mbar_init(&acc_empty_bar[s], 256); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(&tmem_base_smem, Cfg::TMEM_COLS);
@@ -147,8 +148,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             }
         }
     } else {
-        // ===================================================================== epilogue (4 warps = 128 rows)
+        // ===================================================================== epilogue (8 warps: 128 rows x 2 column halves)
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;          // which half of the tile's columns this warp drains
         const int row = q * 32 + lane;
         const int tw = row & (TW - 1);
         const int th = (row >> p.lw) & (TH - 1);
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                 if constexpr (BN == 160) {
                     constexpr int HALF = BN / 2;
 #pragma unroll 1
-                    for (int j = 0; j < HALF; j += 16) {
+                    for (int j = half ? 48 : 0; j < (half ? HALF : 48); j += 16) {
                         uint32_t va[16], vg[16];
                         tmem_ld16(taddr + j, va);
                         tmem_ld16(taddr + HALF + j, vg);
@@ -195,9 +197,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                     }
                 }
             } else {
-                constexpr int CH = BN >= 32 ? 32 : 16;
+                constexpr int HALFN = BN >= 32 ? BN / 2 : BN;
+                constexpr int CH = (HALFN % 32 == 0) ? 32 : 16;
+                const int c_end = half * HALFN + HALFN < BN ? half * HALFN + HALFN : BN;
 #pragma unroll 1
-                for (int c = 0; c < BN; c += CH) {
+                for (int c = half * HALFN; c < c_end; c += CH) {
                     uint32_t v[32];
                     if constexpr (CH == 32) {
                         tmem_ld32(taddr + c, v);

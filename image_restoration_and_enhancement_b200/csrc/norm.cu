@@ -21,6 +21,7 @@ struct GnParams {
     int tpr;                   // threads per pixel row = C / 8
     int rpb;                   // pixel rows handled concurrently by a block
     long long pix_per_block;
+    int n_blocks;              // statistics blocks per image (<= RG_GN_MAX_BLOCKS)
 };
 
 __device__ __forceinline__ void load8(const GnParams& p, int n, long long pix, int c0, float (&v)[8]) {
@@ -42,12 +43,18 @@ __device__ __forceinline__ void load8(const GnParams& p, int n, long long pix, i
     }
 }
 
+// workspace layout (floats): [N counters (int)] [N][G][2] (mean, rstd) [N][blocks][G][2] partial (sum, sumsq)
+__device__ __forceinline__ float* gn_final(const GnParams& p) { return p.sums + ((p.N + 3) & ~3); }
+__device__ __forceinline__ float* gn_partials(const GnParams& p) { return gn_final(p) + (long long)p.N * p.groups * 2; }
+
+// Deterministic, batch-invariant statistics: every block reduces a fixed slice of one image in a fixed order and
+// writes one (sum, sumsq) pair per group to partials[n][block][group]; the apply kernel combines the partials in
+// block order in fp64.  No atomics anywhere, so a run is bitwise reproducible and an image's result does not depend
+// on how many other images share the launch.
 // grid = (blocks_per_image, N); block = tpr * rpb threads
 __global__ void __launch_bounds__(512) gn_stats_kernel(const GnParams p) {
-    extern __shared__ float s_acc[];          // [groups][2]
+    extern __shared__ float s_red[];          // [rpb][tpr][16] thread partials, then [C][2] channel sums
     const int n = blockIdx.y;
-    for (int i = threadIdx.x; i < p.groups * 2; i += blockDim.x) s_acc[i] = 0.f;
-    __syncthreads();
     const int tc = threadIdx.x % p.tpr, tr = threadIdx.x / p.tpr;
     const int c0 = tc * 8;
     float s[8], ss[8];
@@ -56,29 +63,62 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const GnParams p) {
     const long long p0 = (long long)blockIdx.x * p.pix_per_block;
     long long p1 = p0 + p.pix_per_block;
     if (p1 > p.HW) p1 = p.HW;
-    if (tr < p.rpb) {
-        for (long long pix = p0 + tr; pix < p1; pix += p.rpb) {
-            float v[8];
-            load8(p, n, pix, c0, v);
+    for (long long pix = p0 + tr; pix < p1; pix += p.rpb) {
+        float v[8];
+        load8(p, n, pix, c0, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s[i] += v[i]; ss[i] += v[i] * v[i]; }
-        }
-        // fold the 8 channels into their (at most two) groups, then one shared atomic per group
-        int g_prev = c0 / p.cpg; float gs = 0.f, gss = 0.f;
+        for (int i = 0; i < 8; ++i) { s[i] += v[i]; ss[i] += v[i] * v[i]; }
+    }
+    float* mine = s_red + ((long long)tr * p.tpr + tc) * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mine[i] = s[i]; mine[8 + i] = ss[i]; }
+    __syncthreads();
+    float* chan = s_red + (long long)p.rpb * p.tpr * 16;      // [C][2]
+    if (tr == 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int g = (c0 + i) / p.cpg;
-            if (g != g_prev) {
-                atomicAdd(&s_acc[g_prev * 2], gs); atomicAdd(&s_acc[g_prev * 2 + 1], gss);
-                gs = 0.f; gss = 0.f; g_prev = g;
+            float a = 0.f, b = 0.f;
+            for (int r = 0; r < p.rpb; ++r) {                 // fixed order over the row slots
+                const float* o = s_red + ((long long)r * p.tpr + tc) * 16;
+                a += o[i]; b += o[8 + i];
             }
-            gs += s[i]; gss += ss[i];
+            chan[(c0 + i) * 2] = a; chan[(c0 + i) * 2 + 1] = b;
         }
-        atomicAdd(&s_acc[g_prev * 2], gs); atomicAdd(&s_acc[g_prev * 2 + 1], gss);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < p.groups * 2; i += blockDim.x)
-        atomicAdd(&p.sums[(long long)n * p.groups * 2 + i], s_acc[i]);
+    float* partials = gn_partials(p);
+    if ((int)threadIdx.x < p.groups) {
+        const int g = threadIdx.x;
+        float a = 0.f, b = 0.f;
+        for (int c = g * p.cpg; c < (g + 1) * p.cpg; ++c) { a += chan[c * 2]; b += chan[c * 2 + 1]; }
+        float* dst = partials + (((long long)n * gridDim.x + blockIdx.x) * p.groups + g) * 2;
+        dst[0] = a; dst[1] = b;
+    }
+    // the block that finishes last for this image combines the partials in block order (fp64): the counter only
+    // elects WHO does it, so the result does not depend on arrival order
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int* counter = reinterpret_cast<int*>(p.sums) + n;
+        const int done = atomicAdd(counter, 1);
+        is_last = (done == (int)gridDim.x - 1);
+        if (is_last) *counter = 0;                            // self-resetting
+    }
+    __syncthreads();
+    if (is_last && (int)threadIdx.x < p.groups) {
+        __threadfence();
+        const int g = threadIdx.x;
+        const volatile float* part = partials + ((long long)n * gridDim.x * p.groups + g) * 2;
+        double sum = 0.0, sq = 0.0;
+        for (int b = 0; b < (int)gridDim.x; ++b) { sum += part[(long long)b * p.groups * 2]; sq += part[(long long)b * p.groups * 2 + 1]; }
+        const double inv_cnt = 1.0 / ((double)p.cpg * (double)p.HW);
+        const double m = sum * inv_cnt;
+        const double var = fmax(sq * inv_cnt - m * m, 0.0);
+        float* fin = gn_final(p) + ((long long)n * p.groups + g) * 2;
+        fin[0] = (float)m;
+        fin[1] = (float)(1.0 / sqrt(var + (double)p.eps));
+    }
 }
 
 __global__ void __launch_bounds__(512) gn_apply_kernel(const GnParams p) {
@@ -87,14 +127,11 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const GnParams p) {
     if (tr >= p.rpb) return;
     const int c0 = tc * 8;
     float sc[8], sh[8];
-    const float inv_cnt = 1.0f / ((float)p.cpg * (float)p.HW);
+    const float* fin = gn_final(p) + (long long)n * p.groups * 2;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = c0 + i, g = c / p.cpg;
-        const float sum = p.sums[((long long)n * p.groups + g) * 2], sq = p.sums[((long long)n * p.groups + g) * 2 + 1];
-        const float mean = sum * inv_cnt;
-        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + p.eps);
+        const float mean = fin[g * 2], rstd = fin[g * 2 + 1];
         sc[i] = rstd * p.gamma[c];
         sh[i] = p.beta[c] - mean * sc[i];
     }
@@ -134,14 +171,15 @@ static int fill_gn(const rg_gn_t* g, GnParams& p, dim3& grid, int& threads) {
     p.tpr = C / 8;
     p.rpb = 256 / p.tpr; if (p.rpb < 1) p.rpb = 1;
     threads = p.tpr * p.rpb;
-    // aim for ~4 waves of blocks over the chip, at least 8 pixels per row slot
-    long long want_blocks = (4LL * sm_count() + g->N - 1) / g->N;
-    long long ppb = (g->HW + want_blocks - 1) / want_blocks;
+    // The split depends on (HW, C) only -- never on N -- so an image's statistics are reduced in the same order
+    // whatever the batch size: at most RG_GN_MAX_BLOCKS blocks per image, at least 8 pixels per row slot.
+    long long ppb = (g->HW + RG_GN_MAX_BLOCKS - 1) / RG_GN_MAX_BLOCKS;
     const long long min_ppb = 8LL * p.rpb;
     if (ppb < min_ppb) ppb = min_ppb;
     ppb = (ppb + p.rpb - 1) / p.rpb * p.rpb;
     p.pix_per_block = ppb;
-    grid = dim3((unsigned)((g->HW + ppb - 1) / ppb), (unsigned)g->N);
+    p.n_blocks = (int)((g->HW + ppb - 1) / ppb);
+    grid = dim3((unsigned)p.n_blocks, (unsigned)g->N);
     return RG_OK;
 }
 
@@ -232,7 +270,15 @@ extern "C" int rg_groupnorm_stats(const rg_gn_t* g, rg_stream_t stream) {
     memset(&p, 0, sizeof(p));
     int rc = fill_gn(g, p, grid, threads);
     if (rc) return rc;
-    gn_stats_kernel<<<grid, threads, p.groups * 2 * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    const size_t smem = ((size_t)threads * 16 + (size_t)p.C * 2) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr_done = true;
+    }
+    cudaError_t me = cudaMemsetAsync(p.sums, 0, (size_t)p.N * sizeof(int), reinterpret_cast<cudaStream_t>(stream));
+    if (me != cudaSuccess) return set_cuda_error(me, "cudaMemsetAsync(groupnorm counters)");
+    gn_stats_kernel<<<grid, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     count_launch();
     return check_launch("gn_stats_kernel");
 }

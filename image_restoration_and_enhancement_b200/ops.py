@@ -17,6 +17,7 @@ from ._lib import (RG_ACT_GEGLU, RG_ACT_NONE, RG_ACT_SILU, RG_DT_BF16, RG_DT_F32
                    RgSched, check)
 
 bf16, f32 = torch.bfloat16, torch.float32
+GN_MAX_BLOCKS = 64        # RG_GN_MAX_BLOCKS in include/restoragen.h
 
 # When set to a list, conv2d / attention append (start_event, end_event, algorithmic_flops, kind) per launch
 # (bench.py's roofline leg); None in normal operation.
@@ -176,8 +177,9 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, grou
     y = torch.empty((N, H, W, Ct), dtype=bf16, device=x1.device)
     raw = torch.empty((N, H, W, Ct), dtype=bf16, device=x1.device) if want_raw else None
     if sums is None:
-        sums = torch.empty((N, groups, 2), dtype=f32, device=x1.device)
-    check(lib.rg_memset_zero(sums.data_ptr(), N * groups * 2 * 4, _stream()), "rg_memset_zero")
+        # RG_GN_WORKSPACE_FLOATS: counters | (mean, rstd) | per-block partials
+        sums = torch.empty((((N + 3) & ~3) + N * groups * 2 + N * GN_MAX_BLOCKS * groups * 2,), dtype=f32,
+                           device=x1.device)
     p = RgGn()
     p.x1, p.C1, p.x2, p.C2 = x1.data_ptr(), C1, _ptr(x2), C2
     p.in_dtype, p.N, p.HW, p.groups, p.eps = _dt(x1), N, H * W, groups, eps

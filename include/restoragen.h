@@ -120,10 +120,15 @@ int rg_softmax_rows(void* x, int64_t rows, int32_t cols, int64_t ld, rg_stream_t
  * K7  GroupNorm (+SiLU), channels-last.  x may be the channel-concatenation of two tensors
  *   (skip connections of the up blocks) -- the concat is never materialised in fp32.
  *   replaces nn.GroupNorm + F.silu.
- *   rg_groupnorm_stats accumulates (sum, sumsq) per (n, group) into sums[N][G][2] (caller zeroes it);
+ *   rg_groupnorm_stats writes per-block (sum, sumsq) partials per (n, group) into the workspace and the last block
+ *   of each image combines them in block order in fp64 into (mean, rstd); the split depends on (HW, C) only and the
+ *   reduction order is fixed, so results are bitwise reproducible and independent of the batch size;
  *   rg_groupnorm_apply writes y = silu?((x-mean)*rstd*gamma+beta) as bf16 and optionally the raw
  *   concatenated input as bf16 (feeds the fused 1x1 shortcut).
  * ------------------------------------------------------------------------------------------- */
+#define RG_GN_MAX_BLOCKS 64
+#define RG_GN_WORKSPACE_FLOATS(N, G) ((((N) + 3) & ~3) + (N) * (G) * 2 + (N) * RG_GN_MAX_BLOCKS * (G) * 2)
+
 typedef struct rg_gn {
     const void* x1; int32_t C1;     /* first source  [N][HW][C1] */
     const void* x2; int32_t C2;     /* second source [N][HW][C2] or NULL/0 */
@@ -131,7 +136,7 @@ typedef struct rg_gn {
     int32_t N; int64_t HW;
     int32_t groups; float eps;
     const float* gamma; const float* beta;   /* [C1+C2] */
-    float* sums;                    /* [N][groups][2] fp32 workspace */
+    float* sums;                    /* workspace of RG_GN_WORKSPACE_FLOATS(N, groups) floats (counters | mean,rstd | partials) */
     void* y;                        /* bf16 [N][HW][C1+C2] */
     void* raw;                      /* bf16 copy of the concatenated input, or NULL */
     int32_t silu;

@@ -55,7 +55,8 @@ def test_batched_call_equals_separate_calls():
     both = pipe(image=imgs, generator=[torch.Generator(device="cuda").manual_seed(42) for _ in range(2)], **kw).images
     for i in range(2):
         one = pipe(image=imgs[i:i + 1], generator=torch.Generator(device="cuda").manual_seed(42), **kw).images
-        assert mc.psnr_u8(both[i:i + 1], one) >= 50.0        # same arithmetic, different tile/batch shapes
+        # every kernel is batch-invariant (fixed reduction orders, GroupNorm split independent of N): bitwise equal
+        assert (both[i:i + 1] == one).all(), f"image {i}: batched vs single PSNR {mc.psnr_u8(both[i:i + 1], one):.2f} dB"
     with pytest.raises(ValueError):
         pipe(image=imgs, strength=1.5, **{k: v for k, v in kw.items() if k != "strength"})
     with pytest.raises(ValueError):
@@ -79,6 +80,6 @@ def test_restoration_pipeline_drop_in():
     assert next(rp.models["denoise"].unet.parameters()).device.type == "cuda"
     assert ops.launch_count() > n0
     again = rp.process(im, ["denoise"], denoise_strength=0.3)["final"]
-    assert mc.psnr_u8(np.array(again), np.array(res["final"])) == float("inf")      # seeded => deterministic
+    assert (np.array(again) == np.array(res["final"])).all()              # seeded => bitwise reproducible
     outs = rp.process_batch([im, im], "denoise", denoise_strength=0.3)
-    assert mc.psnr_u8(np.array(outs[0]), np.array(res["final"])) >= 50.0
+    assert (np.array(outs[0]) == np.array(res["final"])).all() and (np.array(outs[1]) == np.array(res["final"])).all()

@@ -1,0 +1,34 @@
+"""Small target for `ncu --set full`: a few launches of the dominant kernels at UNet batch-16 shapes."""
+import sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import torch
+import kernel_cases as kc
+from image_restoration_and_enhancement_b200 import ops
+
+which = sys.argv[1] if len(sys.argv) > 1 else "conv"
+torch.manual_seed(0)
+if which == "conv":          # resnet conv 320->320 3x3 at 64x64, 16 samples: M=65536, N=320, K=2880 (120.8 GFLOP)
+    x = torch.randn((16, 64, 64, 320), device="cuda").to(torch.bfloat16)
+    w = (torch.randn((320, 2880), device="cuda") / 53.0).to(torch.bfloat16)
+    b = torch.randn((320,), device="cuda")
+    for _ in range(4):
+        ops.conv2d(x, w, kh=3, kw=3, pad_t=1, pad_l=1, bias=b, out_bf16=True)
+elif which == "linear":      # attention out-projection with fp32 residual in/out: M=65536, N=320, K=320
+    x = torch.randn((65536, 320), device="cuda").to(torch.bfloat16)
+    w = (torch.randn((320, 320), device="cuda") / 18.0).to(torch.bfloat16)
+    r = torch.randn((65536, 320), device="cuda")
+    for _ in range(4):
+        ops.linear(x, w, res=r, out_f32=r.view(1, 1, 65536, 320))
+elif which == "attn":        # self-attention at 64x64 latents: B=16, 8 heads, d=40, N=4096
+    qkv = torch.randn((16, 4096, 3, 8, 40), device="cuda").to(torch.bfloat16)
+    for _ in range(3):
+        ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], 40 ** -0.5)
+elif which == "gn":
+    x = torch.randn((16, 64, 64, 320), device="cuda")
+    g = torch.ones(320, device="cuda"); bta = torch.zeros(320, device="cuda")
+    for _ in range(3):
+        ops.groupnorm(x, g, bta, silu=True)
+torch.cuda.synchronize()
+print("done", which)
