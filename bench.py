@@ -247,10 +247,10 @@ def conv_roofline(pipe, dev) -> dict:
     allrecs, ops.PROFILE = ops.PROFILE, None
     recs = [r for r in allrecs if r[3] == "gemm"]
     att = [r for r in allrecs if r[3] == "attention"]
-    tot_ms = sum(a.elapsed_time(b) for a, b, _, _ in recs)
-    tot_flop = sum(f for _, _, f, _ in recs)
-    att_ms = sum(a.elapsed_time(b) for a, b, _, _ in att)
-    att_flop = sum(f for _, _, f, _ in att)
+    tot_ms = sum(r[0].elapsed_time(r[1]) for r in recs)
+    tot_flop = sum(r[2] for r in recs)
+    att_ms = sum(r[0].elapsed_time(r[1]) for r in att)
+    att_flop = sum(r[2] for r in att)
     achieved = tot_flop / (tot_ms / 1e3) / 1e12 if tot_ms > 0 else 0.0
     traffic = None
     tp = ROOT / "profiles" / "conv_gemm_traffic.json"

@@ -1,12 +1,22 @@
 // K5/K6: fused flash-style attention for sm_100a.  O = softmax(scale * Q K^T) V per (batch, head).
 //
-// One CTA owns 128 query rows of one (batch, head) and walks the keys in tiles of BKV:
-//   warp 0      TMA producer: Q once, then K/V tiles through a 2-stage ring
-//   warp 1      tcgen05.mma issuer:  S = Q K^T  (M=128, N=BKV, K=d)  into TMEM columns [0, BKV)
-//                                    Opart = P V (M=128, N=DV,  K=BKV) into TMEM columns [128, 128+DV)
-//   warps 2..5  softmax: thread r owns query row r (TMEM lane r), so row max / row sum need no shuffles;
-//               P is written to shared memory as the bf16 K-major SWIZZLE_128B A operand of the second MMA;
-//               the running output lives in fp32 registers and is rescaled online.
+// Persistent kernel, one CTA per SM.  A work item is 256 query rows (two 128-row tiles) of one (batch, head); the
+// CTA walks the keys in tiles of BKV for both query tiles at once, so the two softmax warpgroups ping-pong on
+// the tensor core and every K/V tile is fetched once per 256 queries.
+//
+//   warps 0..3   softmax warpgroup of query tile 0   (thread r owns query row r = TMEM lane r: no shuffles)
+//   warps 4..7   softmax warpgroup of query tile 1
+//   warp  8      TMA producer: Q tiles once per item, K/V tiles through a STAGES-deep ring
+//   warp  9      tcgen05.mma issuer:  S_t = Q_t K^T  (M=128, N=BKV, K=d)   -> TMEM columns of S_t
+//                                     O_t += P_t V   (M=128, N=DV,  K=BKV) -> TMEM columns of O_t
+//
+// S is double-buffered per query tile (SBUF = 2): S_t(j+1) is computed while the warpgroup is still busy with
+// S_t(j), so the softmax threads never wait for the tensor core and the MUFU (exp) pipe is the only limiter.
+// Everything between the two GEMMs stays in tensor memory: the softmax threads read S with tcgen05.ld, write the
+// bf16 probabilities P back over the same columns with tcgen05.st, and the second GEMM takes P as its A operand
+// straight from TMEM (no shared-memory round trip, no swizzled stores).  O accumulates in TMEM across the whole
+// key loop; the running maximum is only raised when a tile exceeds it by more than 2^8 (lazy rescale), in which
+// case the owning warp waits for the previous P V to retire and rescales its O rows in TMEM before publishing P.  exp is ex2.approx on pre-scaled logits.
 // Head dims that are not a multiple of 64 (40, 80, 160 in SD-1.5) are handled by the TMA engine: the tensor
 // map's innermost extent is d, so the rest of each 64-wide box is zero-filled in shared memory.
 // V is consumed directly as an MN-major B operand -- no transpose anywhere.
@@ -20,10 +30,13 @@ struct AttnParams {
     __nv_bfloat16* out;
     long long osb, ost, osh;
     int Nq, Nk, d;
+    int heads, n_qpairs, n_items;
     float scale_log2;     // scale * log2(e)
+    long long* trace;     // debug only (rg_debug_attn_trace): per-tile clock64 stamps of CTA 0, else nullptr
 };
 
-constexpr int TMEM_COLS_FOR(int dv) { return dv <= 128 ? 256 : 512; }
+constexpr int kTraceTiles = 64, kTraceStamps = 8;
+#define RG_STAMP(k) do { if (tr && j < kTraceTiles) tr[((warp * kTraceTiles) + j) * kTraceStamps + (k)] = clock64(); } while (0)
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -36,211 +49,326 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
     return y;
 }
 
-template <int DKA, int DV, int BKV>
+template <int DKA, int DV, int BKV, int SBUF, bool PSEP, int STAGES>
 struct AttnCfg {
-    static constexpr int Q_BYTES = DKA * 128 * 128;
+    static constexpr int Q_TILE_BYTES = DKA * 128 * 128;           // one 128-query tile: DKA atoms of [128][64] bf16
     static constexpr int KV_ATOM_BYTES = BKV * 128;
     static constexpr int K_BYTES = DKA * KV_ATOM_BYTES;
     static constexpr int V_BYTES = DKA * KV_ATOM_BYTES;
-    static constexpr int P_BYTES = (BKV / 64) * 128 * 128;
-    static constexpr int STAGES = 2;
-    static constexpr int TILE_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + P_BYTES;
+    static constexpr int STAGE_BYTES = K_BYTES + V_BYTES;
+    static constexpr int TILE_BYTES = 2 * Q_TILE_BYTES + STAGES * STAGE_BYTES;
     // barriers live behind the tiles; there is no static shared memory, so the dynamic window starts 1024-aligned
-    // (checked at run time) and no alignment slack is needed: d=40 uses 112.1 KB and two CTAs share an SM
-    static constexpr int SMEM_BYTES = TILE_BYTES + 128;
-    static constexpr int MIN_CTAS = (2 * (SMEM_BYTES + 1024) <= 228 * 1024 && TMEM_COLS_FOR(DV) <= 256) ? 2 : 1;
-    static constexpr int TMEM_COLS = TMEM_COLS_FOR(DV);
-    static constexpr int O_COL = 128;
+    static constexpr int SMEM_BYTES = TILE_BYTES + 256;
+    static constexpr int O_STRIDE = (DV + 31) / 32 * 32;
+    // TMEM columns: S_t[buf] at (t*SBUF+buf)*BKV.  PSEP: P_t has its own BKV/2 columns (two bf16 per column), so
+    // S_t(G+SBUF) can be issued as soon as S_t(G) is in registers and runs under the softmax of tile G; otherwise P_t
+    // is written over S_t and the next score GEMM is issued in order behind O_t += P_t V.
+    static constexpr int P_COL = 2 * SBUF * BKV;
+    static constexpr int P_STRIDE = PSEP ? BKV / 2 : 0;
+    static constexpr int O_COL = P_COL + 2 * P_STRIDE;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int NBAR = 2 + 4 * SBUF + 4 + 2 * STAGES;
+    static_assert(O_COL + 2 * O_STRIDE <= 512, "TMEM budget");
+    static_assert(NBAR * 8 + 8 <= 256, "barrier area");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(BKV == 64 || BKV == 128, "BKV");
+    static_assert(SBUF == 1 || SBUF == 2, "SBUF");
+    static_assert(PSEP || SBUF == 1, "aliased P implies a single score buffer");
+    static_assert(!PSEP || STAGES >= SBUF + 1, "SBUF tiles of score look-ahead need SBUF+1 K/V stages");
 };
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;
+constexpr float kLazyRescale = 8.0f;       // raise the running max only when a tile exceeds it by > 2^8
 
-template <int DKA, int DV, int BKV>
-__global__ void __launch_bounds__(kAttnThreads, AttnCfg<DKA, DV, BKV>::MIN_CTAS)
-attention_kernel(const __grid_constant__ AttnParams p) {
-    using Cfg = AttnCfg<DKA, DV, BKV>;
+// All barrier phases are indexed by the CTA-global key-tile counter G = (items done) * n_kv + j, which is also the
+// K/V ring position; score buffer G % SBUF is used for the (G / SBUF)-th time.
+template <int DKA, int DV, int BKV, int SBUF, bool PSEP, int STAGES>
+__global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
+    using Cfg = AttnCfg<DKA, DV, BKV, SBUF, PSEP, STAGES>;
     extern __shared__ __align__(16) uint8_t smem[];                    // window-relative base 0: no static smem
     if ((smem_u32(smem) & 1023u) != 0) __trap();                       // SWIZZLE_128B tiles need 1024-B alignment
-    uint8_t* sQ = smem;
-    uint8_t* sKV = sQ + Cfg::Q_BYTES;                                  // [stage][K | V]
-    uint8_t* sP = sKV + Cfg::STAGES * (Cfg::K_BYTES + Cfg::V_BYTES);
+    uint8_t* sQ = smem;                                                // [tile][atom][128][64]
+    uint8_t* sKV = sQ + 2 * Cfg::Q_TILE_BYTES;                         // [stage][K | V]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::TILE_BYTES);
-    uint64_t& q_full = bars[0]; uint64_t& s_full = bars[1]; uint64_t& p_full = bars[2]; uint64_t& o_full = bars[3];
-    uint64_t* kv_full = bars + 4; uint64_t* kv_empty = bars + 6;
-    uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t& q_full = bars[0]; uint64_t& q_empty = bars[1];
+    uint64_t* s_full = bars + 2;                       // [t][buf]  S_t(G) accumulated              (tensor core -> softmax)
+    uint64_t* s_free = s_full + 2 * SBUF;              // [t][buf]  S_t(G) copied to registers      (softmax -> tensor core)
+    uint64_t* p_full = s_free + 2 * SBUF;              // [t]       P_t(G) stored, O_t rescaled     (softmax -> tensor core)
+    uint64_t* pv_done = p_full + 2;                    // [t]       O_t += P_t(G) V retired         (tensor core -> softmax)
+    uint64_t* kv_full = pv_done + 2; uint64_t* kv_empty = kv_full + STAGES;
+    uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(kv_empty + STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
     const int n_kv = (p.Nk + BKV - 1) / BKV;
 
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap); }
-    if (warp == 1 && lane == 0) {
-        mbar_init(&q_full, 1); mbar_init(&s_full, 1); mbar_init(&p_full, 128); mbar_init(&o_full, 1);
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    if (warp == 8 && lane == 0) { tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap); }
+    if (warp == 9 && lane == 0) {
+        mbar_init(&q_full, 1); mbar_init(&q_empty, 1);
+        for (int i = 0; i < 2 * SBUF; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128); }
+        for (int t = 0; t < 2; ++t) { mbar_init(&p_full[t], 128); mbar_init(&pv_done[t], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(&tmem_base_smem, Cfg::TMEM_COLS);
+    if (warp == 0) tmem_alloc(&tmem_base_smem, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    if (warp == 0) {
+    if (warp == 8) {
+        // ===================================================================== TMA producer
         if (lane == 0) {
-            mbar_expect_tx(&q_full, Cfg::Q_BYTES);
+            uint32_t g = 0, it = 0;                                     // g: K/V tiles loaded so far (ring position)
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+                const int qp = item % p.n_qpairs, bh = item / p.n_qpairs;
+                const int h = bh % p.heads, b = bh / p.heads;
+                const int q0 = qp * 256;
+                if (it > 0) mbar_wait(&q_empty, (it - 1) & 1);          // previous item's last S GEMM has read Q
+                mbar_expect_tx(&q_full, 2 * Cfg::Q_TILE_BYTES);
 #pragma unroll
-            for (int a = 0; a < DKA; ++a) tma_load_4d(sQ + a * 128 * 128, &p.qmap, &q_full, a * 64, h, q0, b);
-            int stage = 0; uint32_t phase = 0;
-            for (int j = 0; j < n_kv; ++j) {
-                mbar_wait(&kv_empty[stage], phase ^ 1);
-                uint8_t* sk = sKV + stage * (Cfg::K_BYTES + Cfg::V_BYTES);
-                uint8_t* sv = sk + Cfg::K_BYTES;
-                mbar_expect_tx(&kv_full[stage], Cfg::K_BYTES + Cfg::V_BYTES);
+                for (int t = 0; t < 2; ++t)
 #pragma unroll
-                for (int a = 0; a < DKA; ++a) {
-                    tma_load_4d(sk + a * Cfg::KV_ATOM_BYTES, &p.kmap, &kv_full[stage], a * 64, h, j * BKV, b);
-                    tma_load_4d(sv + a * Cfg::KV_ATOM_BYTES, &p.vmap, &kv_full[stage], a * 64, h, j * BKV, b);
+                    for (int a = 0; a < DKA; ++a)
+                        tma_load_4d(sQ + t * Cfg::Q_TILE_BYTES + a * 128 * 128, &p.qmap, &q_full, a * 64, h,
+                                    q0 + t * 128, b);
+                for (int j = 0; j < n_kv; ++j, ++g) {
+                    const uint32_t stage = g % STAGES, phase = (g / STAGES) & 1;
+                    mbar_wait(&kv_empty[stage], phase ^ 1);
+                    uint8_t* sk = sKV + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sv = sk + Cfg::K_BYTES;
+                    mbar_expect_tx(&kv_full[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+                    for (int a = 0; a < DKA; ++a) {
+                        tma_load_4d(sk + a * Cfg::KV_ATOM_BYTES, &p.kmap, &kv_full[stage], a * 64, h, j * BKV, b);
+                        tma_load_4d(sv + a * Cfg::KV_ATOM_BYTES, &p.vmap, &kv_full[stage], a * 64, h, j * BKV, b);
+                    }
                 }
-                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 9) {
+        // ===================================================================== MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);    // Q (K-major) x K (K-major)
-            constexpr uint32_t idesc_o = umma_idesc_bf16(128, DV, 0, 1);     // P (K-major) x V (MN-major)
-            const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + Cfg::O_COL;
-            mbar_wait(&q_full, 0);
-            int stage = 0; uint32_t phase = 0;
-            for (int j = 0; j < n_kv; ++j) {
-                mbar_wait(&kv_full[stage], phase);
+            constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);    // Q (K-major smem) x K (K-major smem)
+            constexpr uint32_t idesc_o = umma_idesc_bf16(128, DV, 0, 1);     // P (TMEM)         x V (MN-major smem)
+            const uint32_t sq = smem_u32(sQ);
+            const uint32_t skv = smem_u32(sKV);
+            auto wait_kv = [&](uint32_t G) {
+                mbar_wait(&kv_full[G % STAGES], (G / STAGES) & 1);
                 tc_fence_after();
-                const uint32_t sk = smem_u32(sKV + stage * (Cfg::K_BYTES + Cfg::V_BYTES));
-                const uint32_t sv = sk + Cfg::K_BYTES;
-                // ---- S = Q K^T over d (DV/16 k-steps; columns >= d are zero in both operands)
-#pragma unroll
-                for (int ks = 0; ks < DV / 16; ++ks) {
-                    const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(sQ) + (ks / 4) * 128 * 128 + (ks % 4) * 32);
-                    const uint64_t bdesc = umma_desc_kmajor_sw128(sk + (ks / 4) * Cfg::KV_ATOM_BYTES + (ks % 4) * 32);
-                    umma_bf16(s_tmem, adesc, bdesc, idesc_s, ks != 0 ? 1u : 0u);
+            };
+            // S_t(G) = Q_t K_G^T
+            auto issue_s = [&](int t, uint32_t G) {
+                const int buf = (int)(G % SBUF);
+                if (PSEP && G >= SBUF) {                         // the warpgroup has copied S_t(G-SBUF) out of this buffer
+                    mbar_wait(&s_free[t * SBUF + buf], (G / SBUF - 1) & 1);
+                    tc_fence_after();
                 }
-                umma_commit(&s_full);
-                // ---- Opart = P V once the softmax warps have published P
-                mbar_wait(&p_full, j & 1);
+                const uint32_t sk = skv + (G % STAGES) * Cfg::STAGE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < DV / 16; ++ks) {           // columns >= d are zero in both operands
+                    const uint64_t adesc = umma_desc_kmajor_sw128(sq + t * Cfg::Q_TILE_BYTES + (ks / 4) * 128 * 128 + (ks % 4) * 32);
+                    const uint64_t bdesc = umma_desc_kmajor_sw128(sk + (ks / 4) * Cfg::KV_ATOM_BYTES + (ks % 4) * 32);
+                    umma_bf16(tmem_base + (t * SBUF + buf) * BKV, adesc, bdesc, idesc_s, ks != 0 ? 1u : 0u);
+                }
+                umma_commit(&s_full[t * SBUF + buf]);
+            };
+            // O_t (+)= P_t(G) V_G
+            auto issue_pv = [&](int t, uint32_t G, uint32_t acc) {
+                mbar_wait(&p_full[t], G & 1);
                 tc_fence_after();
+                const uint32_t sv = skv + (G % STAGES) * Cfg::STAGE_BYTES + Cfg::K_BYTES;
+                const uint32_t p_tmem = PSEP ? tmem_base + Cfg::P_COL + t * Cfg::P_STRIDE : tmem_base + t * BKV;
 #pragma unroll
                 for (int ks = 0; ks < BKV / 16; ++ks) {
-                    const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(sP) + (ks / 4) * 128 * 128 + (ks % 4) * 32);
                     // 16 kv rows per k-step = 2 groups of 8 rows (1024 B each); 64-wide d blocks are KV_ATOM_BYTES apart
                     const uint64_t bdesc = umma_desc_mnmajor_sw128(sv + ks * 2048, Cfg::KV_ATOM_BYTES, 1024);
-                    umma_bf16(o_tmem, adesc, bdesc, idesc_o, ks != 0 ? 1u : 0u);
+                    // P: two bf16 per 32-bit TMEM column -> 16 keys = 8 columns
+                    umma_bf16_ts(tmem_base + Cfg::O_COL + t * Cfg::O_STRIDE, p_tmem + ks * 8, bdesc, idesc_o,
+                                 (acc | (uint32_t)ks) != 0 ? 1u : 0u);
                 }
-                umma_commit(&o_full);
-                umma_commit(&kv_empty[stage]);
-                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                umma_commit(&pv_done[t]);
+            };
+            uint32_t g0 = 0, it = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it, g0 += n_kv) {
+                mbar_wait(&q_full, it & 1);
+                tc_fence_after();
+                if constexpr (!PSEP) {
+                    wait_kv(g0);
+                    issue_s(0, g0); issue_s(1, g0);
+                    if (n_kv == 1) umma_commit(&q_empty);
+                    for (int j = 0; j < n_kv; ++j) {
+                        const uint32_t G = g0 + j;
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            issue_pv(t, G, j > 0 ? 1u : 0u);
+                            if (t == 1) umma_commit(&kv_empty[G % STAGES]);   // K_G / V_G consumed once these retire
+                            if (j + 1 < n_kv) {                               // in order behind P_t(G) V: P aliases S_t
+                                if (t == 0) wait_kv(G + 1);
+                                issue_s(t, G + 1);
+                                if (t == 1 && j + 2 == n_kv) umma_commit(&q_empty);
+                            }
+                        }
+                    }
+                } else {
+                    for (int j = 0; j < SBUF && j < n_kv; ++j) {              // SBUF score tiles of look-ahead
+                        wait_kv(g0 + j);
+                        issue_s(0, g0 + j); issue_s(1, g0 + j);
+                        if (j + 1 == n_kv) umma_commit(&q_empty);
+                    }
+                    for (int j = 0; j < n_kv; ++j) {
+                        const uint32_t G = g0 + j;
+                        if (j + SBUF < n_kv) {
+                            wait_kv(G + SBUF);
+                            issue_s(0, G + SBUF); issue_s(1, G + SBUF);
+                            if (j + SBUF + 1 == n_kv) umma_commit(&q_empty);
+                        }
+                        issue_pv(0, G, j > 0 ? 1u : 0u);
+                        issue_pv(1, G, j > 0 ? 1u : 0u);
+                        umma_commit(&kv_empty[G % STAGES]);
+                    }
+                }
             }
         }
     } else {
-        const int qd = warp & 3;
+        // ===================================================================== softmax warpgroups
+        const int t = warp >> 2, qd = warp & 3;
         const int row = qd * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-        const uint32_t s_tmem = tmem_base + lane_addr, o_tmem = tmem_base + lane_addr + Cfg::O_COL;
-        float o_acc[DV];
+        const uint32_t s_tmem0 = tmem_base + lane_addr + t * SBUF * BKV;
+        const uint32_t p_tmem0 = tmem_base + lane_addr + Cfg::P_COL + t * Cfg::P_STRIDE;
+        const uint32_t o_tmem = tmem_base + lane_addr + Cfg::O_COL + t * Cfg::O_STRIDE;
+        const float sl = p.scale_log2;
+        uint32_t g0 = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, g0 += n_kv) {
+            const int qp = item % p.n_qpairs, bh = item / p.n_qpairs;
+            const int h = bh % p.heads, b = bh / p.heads;
+            float m_run = -INFINITY, l_run = 0.f;
+            long long* tr = (p.trace && blockIdx.x == 0 && lane == 0 && g0 == 0) ? p.trace : nullptr;
+            for (int j = 0; j < n_kv; ++j) {
+                const uint32_t G = g0 + j;
+                RG_STAMP(0);
+                const int buf = (int)(G % SBUF);
+                const uint32_t s_tmem = s_tmem0 + buf * BKV;
+                const uint32_t p_tmem = PSEP ? p_tmem0 : s_tmem;
+                mbar_wait(&s_full[t * SBUF + buf], (G / SBUF) & 1);
+                tc_fence_after();
+                RG_STAMP(1);
+                float s[BKV];
+                {
+                    uint32_t (&su)[BKV] = reinterpret_cast<uint32_t (&)[BKV]>(s);
 #pragma unroll
-        for (int i = 0; i < DV; ++i) o_acc[i] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f;
-        uint8_t* p_row = sP + row * 128;
-        const int sw = row & 7;
-
-        for (int j = 0; j < n_kv; ++j) {
-            mbar_wait(&s_full, j & 1);
-            tc_fence_after();
-            const int kv_left = p.Nk - j * BKV;              // columns >= kv_left are padding
-            const bool full = kv_left >= BKV;                // warp-uniform: only the last tile can be ragged
-            // ---- pass 1: row max of the raw logits
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < BKV; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(s_tmem + c, v);
-                tmem_ld_wait();
-                if (full) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c + i < kv_left) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    for (int c = 0; c < BKV; c += 32) tmem_ld32(s_tmem + c, reinterpret_cast<uint32_t (&)[32]>(su[c]));
+                    tmem_ld_wait();
                 }
-            }
-            const float m_new = fmaxf(m_run, mx * p.scale_log2);
-            const float alpha = ex2_approx(m_run - m_new);
-            // ---- pass 2: p = 2^(s*scale*log2e - m), row sum, bf16 P -> swizzled smem
-            float l_tile = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < BKV; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(s_tmem + c, v);
-                tmem_ld_wait();
-                float pv[32];
-                if (full) {
+                RG_STAMP(2);
+                if constexpr (PSEP) {                            // the buffer can take S_t(G+SBUF) now
+                    tc_fence_before();
+                    mbar_arrive(&s_free[t * SBUF + buf]);
+                }
+                const int kv_left = p.Nk - j * BKV;              // columns >= kv_left are padding
+                if (kv_left < BKV) {                             // warp-uniform: only the last tile can be ragged
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        pv[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
-                        l_tile += pv[i];
-                    }
-                } else {
+                    for (int i = 0; i < BKV; ++i)
+                        if (i >= kv_left) s[i] = -INFINITY;
+                }
+                float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float e = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
-                        pv[i] = (c + i < kv_left) ? e : 0.f;
-                        l_tile += pv[i];
+                for (int i = 4; i < BKV; i += 8) {
+                    mx0 = max3(mx0, s[i], s[i + 1]);
+                    mx1 = max3(mx1, s[i + 2], s[i + 3]);
+                    if (i + 4 < BKV) {
+                        mx2 = max3(mx2, s[i + 4], s[i + 5]);
+                        mx3 = max3(mx3, s[i + 6], s[i + 7]);
                     }
                 }
+                const float cand = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl;
+                // O_t and the P_t buffer must be quiescent before they are touched.  Aliased P: S_t(G) was issued
+                // behind O_t += P_t(G-1) V, so its arrival already implies that.  PSEP: wait for phase G-1 of pv_done
+                // (phase G-2 was waited for at the previous tile, so the parity cannot alias) -- as late as possible:
+                // right before the P stores, or before a (rare) rescale of O_t.
+                bool quiescent = !PSEP || G == 0;
+                if (j == 0) {
+                    m_run = cand;
+                } else {
+                    const bool need = cand > m_run + kLazyRescale;
+                    if (__any_sync(0xffffffffu, need)) {
+                        if (!quiescent) { mbar_wait(&pv_done[t], (G - 1) & 1); tc_fence_after(); quiescent = true; }
+                        const float alpha = need ? ex2_approx(m_run - cand) : 1.0f;
+                        if (need) { m_run = cand; l_run *= alpha; }
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int kc = (c >> 3) + g;             // 16-byte chunk index along kv
-                    uint8_t* dst = p_row + (kc >> 3) * (128 * 128) + (((kc & 7) ^ sw) << 4);
-                    *reinterpret_cast<uint4*>(dst) =
-                        make_uint4(pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]), pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]),
-                                   pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]), pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]));
+                        for (int c = 0; c < DV; c += 16) {
+                            uint32_t v[16];
+                            tmem_ld16(o_tmem + c, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                            tmem_st16(o_tmem + c, v);
+                        }
+                    }
                 }
+                RG_STAMP(3);
+                const float neg_m = -m_run;
+                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+                uint32_t pk[BKV / 2];
+#pragma unroll
+                for (int i = 0; i < BKV; i += 4) {
+                    const float e0 = ex2_approx(fmaf(s[i], sl, neg_m));
+                    const float e1 = ex2_approx(fmaf(s[i + 1], sl, neg_m));
+                    const float e2 = ex2_approx(fmaf(s[i + 2], sl, neg_m));
+                    const float e3 = ex2_approx(fmaf(s[i + 3], sl, neg_m));
+                    l0 += e0; l1 += e1; l2 += e2; l3 += e3;
+                    pk[i / 2] = pack_bf16x2(e0, e1);
+                    pk[i / 2 + 1] = pack_bf16x2(e2, e3);
+                    if (!PSEP && (i & 31) == 28)                 // aliased: stream each finished 32-key chunk out
+                        tmem_st16(p_tmem + (i - 28) / 2, reinterpret_cast<uint32_t (&)[16]>(pk[(i - 28) / 2]));
+                }
+                RG_STAMP(4);
+                if constexpr (PSEP) {
+                    if (!quiescent) { mbar_wait(&pv_done[t], (G - 1) & 1); tc_fence_after(); }
+                    RG_STAMP(5);
+#pragma unroll
+                    for (int c = 0; c < BKV / 2; c += 16) tmem_st16(p_tmem + c, reinterpret_cast<uint32_t (&)[16]>(pk[c]));
+                }
+                l_run += (l0 + l1) + (l2 + l3);
+                tmem_st_wait();
+                RG_STAMP(6);
+                tc_fence_before();
+                mbar_arrive(&p_full[t]);
+                RG_STAMP(7);
             }
-            l_run = l_run * alpha + l_tile;
-            m_run = m_new;
-            fence_proxy_async_smem();        // generic-proxy writes of P -> visible to the tensor core (async proxy)
-            tc_fence_before();
-            mbar_arrive(&p_full);
-            // ---- fold Opart into the running output
-            mbar_wait(&o_full, j & 1);
+            // ---- item epilogue: O_t / l -> bf16 -> global
+            mbar_wait(&pv_done[t], (g0 + n_kv - 1) & 1);
             tc_fence_after();
+            const int tq = qp * 256 + t * 128 + row;
+            const float inv = 1.0f / l_run;
+            __nv_bfloat16* dst = p.out + (long long)b * p.osb + (long long)tq * p.ost + (long long)h * p.osh;
 #pragma unroll
             for (int c = 0; c < DV; c += 16) {
                 uint32_t v[16];
                 tmem_ld16(o_tmem + c, v);
                 tmem_ld_wait();
+                if (tq < p.Nq) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) o_acc[c + i] = o_acc[c + i] * alpha + __uint_as_float(v[i]);
-            }
-            tc_fence_before();
-        }
-        const int t = q0 + row;
-        if (t < p.Nq) {
-            const float inv = 1.0f / l_run;
-            __nv_bfloat16* dst = p.out + (long long)b * p.osb + (long long)t * p.ost + (long long)h * p.osh;
-#pragma unroll
-            for (int c = 0; c < DV; c += 8) {
-                if (c < p.d) {
-                    *reinterpret_cast<uint4*>(dst + c) =
-                        make_uint4(pack_bf16x2(o_acc[c] * inv, o_acc[c + 1] * inv), pack_bf16x2(o_acc[c + 2] * inv, o_acc[c + 3] * inv),
-                                   pack_bf16x2(o_acc[c + 4] * inv, o_acc[c + 5] * inv), pack_bf16x2(o_acc[c + 6] * inv, o_acc[c + 7] * inv));
+                    for (int g = 0; g < 16; g += 8) {
+                        if (c + g < p.d) {
+                            *reinterpret_cast<uint4*>(dst + c + g) = make_uint4(
+                                pack_bf16x2(__uint_as_float(v[g]) * inv, __uint_as_float(v[g + 1]) * inv),
+                                pack_bf16x2(__uint_as_float(v[g + 2]) * inv, __uint_as_float(v[g + 3]) * inv),
+                                pack_bf16x2(__uint_as_float(v[g + 4]) * inv, __uint_as_float(v[g + 5]) * inv),
+                                pack_bf16x2(__uint_as_float(v[g + 6]) * inv, __uint_as_float(v[g + 7]) * inv));
+                        }
+                    }
                 }
             }
+            tc_fence_before();       // O_t reads are ordered before the next item's p_full arrival (-> next PV with acc=0)
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
+
+static long long* g_attn_trace = nullptr;
 
 static int encode_qkv_map(CUtensorMap* m, const void* base, int d, int heads, long long tokens, int B, long long sh,
                           long long st, long long sb, int rows) {
@@ -252,13 +380,13 @@ static int encode_qkv_map(CUtensorMap* m, const void* base, int d, int heads, lo
                              CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int DKA, int DV, int BKV>
+template <int DKA, int DV, int BKV, int SBUF, bool PSEP, int STAGES>
 static int launch_attn(const rg_attn_t* a, cudaStream_t stream) {
-    using Cfg = AttnCfg<DKA, DV, BKV>;
+    using Cfg = AttnCfg<DKA, DV, BKV, SBUF, PSEP, STAGES>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(attention_kernel<DKA, DV, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(attention_kernel<DKA, DV, BKV, SBUF, PSEP, STAGES>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attention_kernel)");
         attr_done = true;
     }
@@ -271,9 +399,15 @@ static int launch_attn(const rg_attn_t* a, cudaStream_t stream) {
     p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
     p.osb = a->o_stride_b; p.ost = a->o_stride_t; p.osh = a->o_stride_h;
     p.Nq = a->Nq; p.Nk = a->Nk; p.d = a->d;
+    p.heads = a->heads;
+    p.n_qpairs = (a->Nq + 255) / 256;
+    const long long items = (long long)p.n_qpairs * a->heads * a->B;
+    if (items > 0x7fffffffLL) return set_error(RG_ERR_ARG, "attention: too many work items");
+    p.n_items = (int)items;
     p.scale_log2 = a->scale * 1.4426950408889634f;
-    dim3 grid((a->Nq + 127) / 128, a->heads, a->B);
-    attention_kernel<DKA, DV, BKV><<<grid, kAttnThreads, Cfg::SMEM_BYTES, stream>>>(p);
+    p.trace = g_attn_trace;
+    const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
+    attention_kernel<DKA, DV, BKV, SBUF, PSEP, STAGES><<<grid, kAttnThreads, Cfg::SMEM_BYTES, stream>>>(p);
     count_launch();
     return check_launch("attention_kernel");
 }
@@ -282,11 +416,16 @@ static int launch_attn(const rg_attn_t* a, cudaStream_t stream) {
 
 using namespace rg;
 
+// Debug hook (not part of the public header): device buffer of 8 warps x 64 tiles x 8 clock64 stamps written by
+// CTA 0 for its first work item; nullptr switches tracing off.
+extern "C" void rg_debug_attn_trace(void* dev_buf) { g_attn_trace = reinterpret_cast<long long*>(dev_buf); }
+
 extern "C" int rg_attention(const rg_attn_t* a, rg_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (!a || !a->q || !a->k || !a->v || !a->out) return set_error(RG_ERR_ARG, "attention: null pointer");
     if (a->d % 8 || a->d < 8 || a->d > 160) return set_error(RG_ERR_ARG, "attention: head dim must be a multiple of 8 in [8,160]");
     if (a->Nq < 1 || a->Nk < 1) return set_error(RG_ERR_ARG, "attention: empty sequence");
+    if (!(a->scale > 0.f)) return set_error(RG_ERR_ARG, "attention: scale must be positive");
     const int64_t st[] = {a->q_stride_b, a->q_stride_t, a->q_stride_h, a->k_stride_b, a->k_stride_t, a->k_stride_h,
                           a->v_stride_b, a->v_stride_t, a->v_stride_h, a->o_stride_b, a->o_stride_t, a->o_stride_h};
     for (int64_t s : st)
@@ -295,9 +434,9 @@ extern "C" int rg_attention(const rg_attn_t* a, rg_stream_t stream_) {
          reinterpret_cast<uintptr_t>(a->out)) & 15)
         return set_error(RG_ERR_ARG, "attention: pointers must be 16-byte aligned");
     const int dv = (a->d + 15) / 16 * 16;
-    if (dv <= 48) return launch_attn<1, 48, 128>(a, stream);
-    if (dv <= 64) return launch_attn<1, 64, 128>(a, stream);
-    if (dv <= 80) return launch_attn<2, 80, 128>(a, stream);
-    if (dv <= 128) return launch_attn<2, 128, 64>(a, stream);
-    return launch_attn<3, 160, 64>(a, stream);
+    if (dv <= 48) return launch_attn<1, 48, 128, 1, true, 4>(a, stream);
+    if (dv <= 64) return launch_attn<1, 64, 128, 1, true, 4>(a, stream);
+    if (dv <= 80) return launch_attn<2, 80, 128, 1, false, 2>(a, stream);
+    if (dv <= 128) return launch_attn<2, 128, 128, 1, false, 2>(a, stream);
+    return launch_attn<3, 160, 64, 1, false, 2>(a, stream);
 }

@@ -32,11 +32,12 @@ def _prof_begin():
     return e
 
 
-def _prof_end(e0, flops, kind):
+def _prof_end(e0, work, kind, desc=""):
+    """``work``: algorithmic FLOPs for gemm / attention, algorithmic bytes for the HBM-bound kernels."""
     if e0 is not None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        PROFILE.append((e0, e1, flops, kind))
+        PROFILE.append((e0, e1, work, kind, desc))
 
 
 def _stream() -> int:
@@ -123,7 +124,9 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, *, kh: int = 1, kw: int = 1, stride
     p.act, p.scale = act, scale
     e0 = _prof_begin()
     check(lib.rg_conv2d(C.byref(p), _stream()), "rg_conv2d")
-    _prof_end(e0, 2.0 * N * OH * OW * Cout * ktot, "gemm")
+    _prof_end(e0, 2.0 * N * OH * OW * Cout * ktot, "gemm",
+              f"conv{kh}x{kw}s{stride} M={N * OH * OW} ({N}x{OH}x{OW}) N={Cout} K={ktot} act={act}"
+              f"{' res' if res is not None else ''}{' f32out' if out_f32 is not None else ''}")
     return out_bf16, out_f32
 
 
@@ -154,7 +157,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, o
     p.scale = scale
     e0 = _prof_begin()
     check(lib.rg_attention(C.byref(p), _stream()), "rg_attention")
-    _prof_end(e0, 4.0 * B * Hh * Nq * Nk * d, "attention")
+    _prof_end(e0, 4.0 * B * Hh * Nq * Nk * d, "attention", f"B={B} H={Hh} Nq={Nq} Nk={Nk} d={d}")
     return out
 
 
@@ -185,16 +188,22 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, grou
     p.in_dtype, p.N, p.HW, p.groups, p.eps = _dt(x1), N, H * W, groups, eps
     p.gamma, p.beta, p.sums = gamma.data_ptr(), beta.data_ptr(), sums.data_ptr()
     p.y, p.raw, p.silu = y.data_ptr(), _ptr(raw), int(silu)
+    e0 = _prof_begin()
     check(lib.rg_groupnorm_stats(C.byref(p), _stream()), "rg_groupnorm_stats")
     check(lib.rg_groupnorm_apply(C.byref(p), _stream()), "rg_groupnorm_apply")
+    isz = x1.element_size()
+    _prof_end(e0, float(N * H * W * Ct) * (2 * isz + 2 + (2 if want_raw else 0)), "groupnorm",
+              f"N={N} HW={H * W} C={Ct} in={'f32' if isz == 4 else 'bf16'} silu={int(silu)} raw={int(want_raw)}")
     return y, raw
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     assert x.is_contiguous() and x.dim() == 2
     y = torch.empty(x.shape, dtype=bf16, device=x.device)
+    e0 = _prof_begin()
     check(_lib.load().rg_layernorm(x.data_ptr(), _dt(x), x.shape[0], x.shape[1], gamma.data_ptr(), beta.data_ptr(),
                                    eps, y.data_ptr(), _stream()), "rg_layernorm")
+    _prof_end(e0, float(x.numel()) * (x.element_size() + 2), "layernorm", f"rows={x.shape[0]} C={x.shape[1]}")
     return y
 
 
