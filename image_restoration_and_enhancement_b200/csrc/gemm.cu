@@ -1,18 +1,27 @@
-// K1-K4: implicit-GEMM convolution / linear layer for sm_100a.
+// K1-K4: implicit-GEMM convolution / linear layer for sm_100a, CTA-pair (cta_group::2) edition.
 //
-//   D[128 x BN] (fp32, TMEM)  +=  A[128 x 64] (bf16, smem via TMA)  x  B[BN x 64]^T (bf16, smem via TMA)
+//   D[256 x N_TILE] (fp32, TMEM of two SMs)  +=  A[256 x 64] (bf16)  x  B[N_TILE x 64]^T (bf16)
+//
+// Why pairs: on B200 a dense GEMM is bound by the L2 -> SM fill rate (about 43 B/clk/SM chip-wide) long before the
+// tensor pipe saturates.  A 128 x 160 single-CTA tile needs 115 B/clk/SM at full MMA rate; a 256 x 320 tile shared
+// by the two SMs of a TPC needs 58 B/clk/SM, because each CTA fetches only its own 128 rows of A and HALF of the B
+// tile, and tcgen05.mma.cta_group::2 reads both halves.
 //
 // * A is never materialised: for every filter tap the TMA engine fetches a {64 ch, TW, TH, TN} box of the
 //   channels-last activation at the tap's spatial offset; out-of-bounds coordinates are zero-filled by the
 //   hardware, which is exactly the convolution's zero padding.  Stride-2 convolutions read four "parity"
 //   views of the input (one tensor map each), so they are plain shifted boxes as well.
-// * B is the packed weight matrix [Cout][taps*Cin (+C2)], K-major.
-// * Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..9 =
-//   epilogue (TMEM -> registers -> global; two warps per TMEM lane quarter, each draining half of the tile's
-//   columns).  The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of
-//   tile i+1.
-// * Epilogue fuses: scale, bias, per-image bias (time embedding), residual add (bf16 or fp32), SiLU,
-//   GEGLU (a * gelu(g)), and writes bf16 and/or fp32, with arbitrary output pixel strides.
+// * B is the packed weight matrix [Cout][taps*Cin (+C2)], K-major.  A tile is NC chunks of BNC columns (one MMA
+//   per chunk and k-step); CTA r of the pair holds rows [r*BNC/2, (r+1)*BNC/2) of every chunk.
+// * Persistent, warp-specialised, one cluster of two CTAs per TPC: warp 0 = TMA producer (both CTAs; all
+//   completion bytes are signalled on the leader's barrier), warp 1 = tcgen05.mma issuer (leader CTA only;
+//   commits are multicast to both CTAs), warps 2..9 = epilogue of the CTA's own 128 accumulator rows.
+// * The accumulator chunks live in a ring of TMEM slots, so the epilogue of tile i overlaps the main loop of
+//   tile i+1 (fully for NC = 1, from the second chunk on for the 2 x 160 tile that uses 3 slots).
+// * Epilogue: TMEM -> registers -> per-warp shared-memory transpose -> row-contiguous global accesses (every
+//   warp instruction touches 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes), fusing scale, bias,
+//   per-image bias (time embedding), residual add (bf16 or fp32), SiLU, GEGLU (a * gelu(g)) and the bf16 and/or
+//   fp32 stores with arbitrary output pixel strides.
 #include "common.cuh"
 #include "internal.h"
 
@@ -28,7 +37,7 @@ struct GemmParams {
     int total_kblk;
     int lw, lh;                       // log2 of the spatial tile (TW, TH); TN = 128 >> (lw+lh)
     int tiles_w, tiles_h, tiles_n;
-    int n_tiles_m, n_tiles_n;
+    int n_pairs_m, n_tiles_n;         // cluster tiles: pairs of 128-pixel tiles x N_TILE-wide column tiles
     int N, OH, OW, Cout;
     const float* bias;
     const float* bias_n;
@@ -43,38 +52,57 @@ struct GemmParams {
     int vec_ok;
 };
 
-template <int BN>
-struct GemmCfg {
-    static constexpr int BM = 128, BK = 64;
-    static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int MAX_STAGES = (227 * 1024 - 1024) / STAGE_BYTES;
-    static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
-    static constexpr int ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
-};
-
 constexpr int kGemmThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kEpiWarps = 8;
+
+template <int BNC, int NC>
+struct GemmCfg {
+    static constexpr int BM = 128, BK = 64;                   // per CTA; the pair computes 256 rows
+    static constexpr int N_TILE = BNC * NC;
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_CHUNK_BYTES = (BNC / 2) * BK * 2;  // this CTA's half of one chunk
+    static constexpr int STAGE_BYTES = A_BYTES + NC * B_CHUNK_BYTES;
+    static constexpr int STAGING_BYTES = kEpiWarps * 2 * 2048;  // per warp: two [32 rows][16 fp32] transpose buffers
+    static constexpr int BAR_BYTES = 512;
+    static constexpr int MAX_STAGES = (227 * 1024 - 1024 - STAGING_BYTES - BAR_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+    static constexpr int SLOTS = 512 / BNC > 4 ? 4 : 512 / BNC;
+    static constexpr int TMEM_COLS = SLOTS * BNC <= 32 ? 32 : SLOTS * BNC <= 64 ? 64 : SLOTS * BNC <= 128 ? 128
+                                   : SLOTS * BNC <= 256 ? 256 : 512;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;
+    static_assert(BNC % 32 == 0 && BNC >= 32 && BNC <= 256, "BNC");
+    static_assert(SLOTS >= NC + (NC > 1 ? 1 : 1), "TMEM ring too small");
+    static_assert((2 * STAGES + 2 * SLOTS) * 8 + 8 <= BAR_BYTES, "barrier area");
+    static_assert(B_CHUNK_BYTES % 1024 == 0, "operand tiles must stay 1024-B aligned");
+};
 
 __device__ __forceinline__ float apply_act(float x, int act) { return act == 1 ? silu_f(x) : x; }
 
-template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
-    using Cfg = GemmCfg<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    // SWIZZLE_128B operand tiles need 1024-byte alignment
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+// geometry of the 128 accumulator rows a CTA owns for one tile
+struct RowGeom {
+    long long off[4];      // element offset of the output pixel of read-phase row i (rows rsub + 8 i)
+    int n[4];
+    unsigned valid;        // bit i: read-phase row i is a real output pixel
+};
 
-    __shared__ __align__(8) uint64_t full_bar[Cfg::STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[Cfg::STAGES];
-    __shared__ __align__(8) uint64_t acc_full_bar[2];
-    __shared__ __align__(8) uint64_t acc_empty_bar[2];
-    __shared__ uint32_t tmem_base_smem;
+template <int BNC, int NC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+conv_gemm_kernel(const __grid_constant__ GemmParams p) {
+    using Cfg = GemmCfg<BNC, NC>;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B operand tiles need 1024-byte alignment; both CTAs of the pair compute the same offset
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);   // leader's are the live ones
+    uint64_t* empty_bar = full_bar + Cfg::STAGES;
+    uint64_t* acc_full = empty_bar + Cfg::STAGES;
+    uint64_t* acc_empty = acc_full + Cfg::SLOTS;                                       // leader's are the live ones
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + Cfg::SLOTS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 5; ++i) tma_prefetch_desc(&p.amap[i]);
@@ -82,221 +110,263 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full_bar[s], 1); mbar_init(&acc_empty_bar[s], 256); }
+        for (int s = 0; s < Cfg::SLOTS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * kEpiWarps); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(&tmem_base_smem, Cfg::TMEM_COLS);
+    if (warp == 2) tmem_alloc_pair(tmem_base_smem, Cfg::TMEM_COLS);
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();                 // barriers of BOTH CTAs are initialised before anyone signals across the pair
     tc_fence_after();
-    const uint32_t tmem_base = tmem_base_smem;
+    const uint32_t tmem_base = *tmem_base_smem;
 
-    const int total_tiles = p.n_tiles_m * p.n_tiles_n;
+    const int total_tiles = p.n_pairs_m * p.n_tiles_n;
     const int TW = 1 << p.lw, TH = 1 << p.lh;
 
     if (warp == 0) {
-        // ===================================================================== TMA producer
+        // ===================================================================== TMA producer (both CTAs)
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_tile = tile / p.n_tiles_n, n_tile = tile - m_tile * p.n_tiles_n;
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+                const int mp = tile / p.n_tiles_n, n_tile = tile - mp * p.n_tiles_n;
+                const int m_tile = 2 * mp + (int)rank;
                 const int twi = m_tile % p.tiles_w;
                 const int rest = m_tile / p.tiles_w;
                 const int thi = rest % p.tiles_h, tni = rest / p.tiles_h;
-                const int w0 = twi * TW, h0 = thi * TH, n0 = tni * (128 >> (p.lw + p.lh));
+                const int w0 = twi * TW, h0 = thi * TH, n0 = tni * (128 >> (p.lw + p.lh));   // n0 >= N: zero fill
+                const int brow = n_tile * Cfg::N_TILE + (int)rank * (BNC / 2);
                 int kblk = 0;
                 for (int it = 0; it < p.n_items; ++it) {
                     const GemmItem item = p.items[it];
                     for (int cb = 0; cb < item.nblk; ++cb, ++kblk) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                        uint8_t* sb = sa + Cfg::A_BYTES;
-                        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                        tma_load_4d(sa, &p.amap[item.map], &full_bar[stage], cb * 64, w0 + item.dw, h0 + item.dh, n0);
-                        tma_load_2d(sb, &p.bmap, &full_bar[stage], kblk * 64, n_tile * BN);
+                        const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                        tma_load_4d_pair(sa, &p.amap[item.map], fb, cb * 64, w0 + item.dw, h0 + item.dh, n0);
+#pragma unroll
+                        for (int c = 0; c < NC; ++c)
+                            tma_load_2d_pair(sa + Cfg::A_BYTES + c * Cfg::B_CHUNK_BYTES, &p.bmap, fb, kblk * 64,
+                                             brow + c * BNC);
                         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+        // ===================================================================== MMA issuer (leader CTA only)
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(256, BNC, 0, 0);
             int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);
+            uint32_t cc = 0;                                   // accumulator chunks started so far (ring position)
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, cc += NC) {
+                uint32_t d_tmem[NC];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const uint32_t slot = (cc + c) % Cfg::SLOTS, use = (cc + c) / Cfg::SLOTS;
+                    mbar_wait(&acc_empty[slot], (use & 1) ^ 1);            // both CTAs have drained this slot
+                    d_tmem[c] = tmem_base + slot * BNC;
+                }
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
                 for (int kb = 0; kb < p.total_kblk; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint64_t adesc = umma_desc_kmajor_sw128(sa);
-                    const uint64_t bdesc = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        // advance 16 bf16 = 32 B along K inside the 128-B swizzle atom: +2 in the (addr >> 4) field
-                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int c = 0; c < NC; ++c) {
+                        const uint64_t bdesc = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES + c * Cfg::B_CHUNK_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            // advance 16 bf16 = 32 B along K inside the 128-B swizzle atom: +2 in the (addr >> 4) field
+                            umma_bf16_pair(d_tmem[c], adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
-                    umma_commit(&empty_bar[stage]);        // frees the smem stage when these MMAs retire
+                    umma_commit_pair(&empty_bar[stage]);        // frees the stage in both CTAs when these MMAs retire
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&acc_full_bar[acc]);            // accumulator ready for the epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#pragma unroll
+                for (int c = 0; c < NC; ++c) umma_commit_pair(&acc_full[(cc + c) % Cfg::SLOTS]);
             }
         }
     } else {
-        // ===================================================================== epilogue (8 warps: 128 rows x 2 column halves)
+        // ===================================================================== epilogue (both CTAs, own 128 rows)
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;          // which half of the tile's columns this warp drains
-        const int row = q * 32 + lane;
-        const int tw = row & (TW - 1);
-        const int th = (row >> p.lw) & (TH - 1);
-        const int tn = row >> (p.lw + p.lh);
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = tile / p.n_tiles_n, n_tile = tile - m_tile * p.n_tiles_n;
+        const int half = (warp - 2) >> 2;          // units are dealt alternately to the two warps of a quarter
+        const int rsub = lane >> 2, quad = lane & 3;
+        float4* st0 = reinterpret_cast<float4*>(staging + (warp - 2) * 4096);
+        float4* st1 = st0 + 128;
+        const int wsw = (lane >> 1) & 3;           // write-phase swizzle of this lane's row
+        const bool geglu = p.act == 2;
+        const uint32_t acc_empty_leader = mapa_shared(smem_u32(acc_empty), 0);
+        uint32_t cc = 0;
+        for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, cc += NC) {
+            const int mp = tile / p.n_tiles_n, n_tile = tile - mp * p.n_tiles_n;
+            const int m_tile = 2 * mp + (int)rank;
             const int twi = m_tile % p.tiles_w;
             const int rest = m_tile / p.tiles_w;
             const int thi = rest % p.tiles_h, tni = rest / p.tiles_h;
-            const int ow = twi * TW + tw, oh = thi * TH + th, n = tni * (128 >> (p.lw + p.lh)) + tn;
-            const bool valid = (ow < p.OW) && (oh < p.OH) && (n < p.N);
-            const long long off = valid ? ((long long)n * p.osn + (long long)oh * p.osh + (long long)ow * p.osw) : 0;
-
-            mbar_wait(&acc_full_bar[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
-
-            if (p.act == 2) {
-                // GEGLU: tile columns [0,BN/2) = a, [BN/2,BN) = gate
-                if constexpr (BN == 160) {
-                    constexpr int HALF = BN / 2;
-#pragma unroll 1
-                    for (int j = half ? 48 : 0; j < (half ? HALF : 48); j += 16) {
-                        uint32_t va[16], vg[16];
-                        tmem_ld16(taddr + j, va);
-                        tmem_ld16(taddr + HALF + j, vg);
-                        tmem_ld_wait();
-                        if (valid) {
-                            const int ca = n_tile * BN + j, cg = ca + HALF, co = n_tile * HALF + j;
-                            uint32_t packed[8];
+            // geometry of this lane's own row (TMEM lane q*32 + lane), then of the 4 rows it handles after the transpose
+            RowGeom g;
+            {
+                const int row = q * 32 + lane;
+                const int ow = twi * TW + (row & (TW - 1));
+                const int oh = thi * TH + ((row >> p.lw) & (TH - 1));
+                const int n = tni * (128 >> (p.lw + p.lh)) + (row >> (p.lw + p.lh));
+                const bool valid = (ow < p.OW) && (oh < p.OH) && (n < p.N);
+                const long long off = valid ? ((long long)n * p.osn + (long long)oh * p.osh + (long long)ow * p.osw) : 0;
+                g.valid = 0;
 #pragma unroll
-                            for (int i = 0; i < 16; i += 2) {
-                                float a0 = __uint_as_float(va[i]) * p.scale + (p.bias ? __ldg(p.bias + ca + i) : 0.f);
-                                float a1 = __uint_as_float(va[i + 1]) * p.scale + (p.bias ? __ldg(p.bias + ca + i + 1) : 0.f);
-                                float g0 = __uint_as_float(vg[i]) * p.scale + (p.bias ? __ldg(p.bias + cg + i) : 0.f);
-                                float g1 = __uint_as_float(vg[i + 1]) * p.scale + (p.bias ? __ldg(p.bias + cg + i + 1) : 0.f);
-                                packed[i / 2] = pack_bf16x2(a0 * gelu_erf_f(g0), a1 * gelu_erf_f(g1));
-                            }
-                            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + off + co);
-                            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-                        }
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    const int src = rsub + 8 * i;
+                    g.off[i] = __shfl_sync(0xffffffffu, off, src);
+                    g.n[i] = __shfl_sync(0xffffffffu, n, src);
+                    g.valid |= (__shfl_sync(0xffffffffu, (int)valid, src) ? 1u : 0u) << i;
                 }
-            } else {
-                constexpr int HALFN = BN >= 32 ? BN / 2 : BN;
-                constexpr int CH = (HALFN % 32 == 0) ? 32 : 16;
-                const int c_end = half * HALFN + HALFN < BN ? half * HALFN + HALFN : BN;
+            }
 #pragma unroll 1
-                for (int c = half * HALFN; c < c_end; c += CH) {
-                    uint32_t v[32];
-                    if constexpr (CH == 32) {
-                        tmem_ld32(taddr + c, v);
-                    } else {
-                        uint32_t v16[16];
-                        tmem_ld16(taddr + c, v16);
+            for (int c = 0; c < NC; ++c) {
+                const uint32_t slot = (cc + c) % Cfg::SLOTS, use = (cc + c) / Cfg::SLOTS;
+                mbar_wait(&acc_full[slot], use & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * BNC;
+                const int ncol0 = n_tile * Cfg::N_TILE + c * BNC;          // first weight row / GEMM column of this chunk
+                if (geglu) {
+                    // unit = 16 value columns followed by their 16 gate columns (host interleave, weights.interleave_geglu)
+#pragma unroll 1
+                    for (int u = half; u < BNC / 32; u += 2) {
+                        if (ncol0 + u * 32 >= p.Cout) break;             // warp-uniform: the rest of the chunk is padding
+                        uint32_t va[16], vg[16];
+                        tmem_ld16(taddr + u * 32, va);
+                        tmem_ld16(taddr + u * 32 + 16, vg);
+                        tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = v16[i];
+                        for (int j = 0; j < 4; ++j) {
+                            st0[lane * 4 + (j ^ wsw)] = make_float4(__uint_as_float(va[4 * j]), __uint_as_float(va[4 * j + 1]),
+                                                                    __uint_as_float(va[4 * j + 2]), __uint_as_float(va[4 * j + 3]));
+                            st1[lane * 4 + (j ^ wsw)] = make_float4(__uint_as_float(vg[4 * j]), __uint_as_float(vg[4 * j + 1]),
+                                                                    __uint_as_float(vg[4 * j + 2]), __uint_as_float(vg[4 * j + 3]));
+                        }
+                        __syncwarp();
+                        const int ca = ncol0 + u * 32 + quad * 4, cg = ca + 16;
+                        const int co = (ncol0 >> 1) + u * 16 + quad * 4;
+                        float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+                        if (p.bias) {
+                            ba = __ldg(reinterpret_cast<const float4*>(p.bias + ca));
+                            bg = __ldg(reinterpret_cast<const float4*>(p.bias + cg));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = rsub + 8 * i;
+                            const float4 a = st0[r * 4 + (quad ^ ((r >> 1) & 3))];
+                            const float4 gt = st1[r * 4 + (quad ^ ((r >> 1) & 3))];
+                            if (g.valid >> i & 1) {
+                                const float y0 = (a.x * p.scale + ba.x) * gelu_erf_f(gt.x * p.scale + bg.x);
+                                const float y1 = (a.y * p.scale + ba.y) * gelu_erf_f(gt.y * p.scale + bg.y);
+                                const float y2 = (a.z * p.scale + ba.z) * gelu_erf_f(gt.z * p.scale + bg.z);
+                                const float y3 = (a.w * p.scale + ba.w) * gelu_erf_f(gt.w * p.scale + bg.w);
+                                *reinterpret_cast<uint2*>(p.out_bf16 + g.off[i] + co) =
+                                    make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                            }
+                        }
+                        __syncwarp();
                     }
-                    tmem_ld_wait();
-                    const int col0 = n_tile * BN + c;
-                    if (valid && col0 < p.Cout) {
-                        const float* bn_row = p.bias_n ? p.bias_n + (long long)n * p.bias_n_ld : nullptr;
-                        if (p.vec_ok && col0 + CH <= p.Cout) {
+                } else {
+                    int ub = 0;                              // staging buffer toggle: one __syncwarp per unit suffices
+#pragma unroll 1
+                    for (int u = half; u < BNC / 16; u += 2, ub ^= 1) {
+                        const int col = ncol0 + u * 16 + quad * 4;
+                        if (ncol0 + u * 16 >= p.Cout) break;             // warp-uniform: the rest of the chunk is padding
+                        uint32_t v[16];
+                        tmem_ld16(taddr + u * 16, v);
+                        tmem_ld_wait();
+                        float4* st = ub ? st1 : st0;
 #pragma unroll
-                            for (int g8 = 0; g8 < CH; g8 += 8) {
-                                float x[8];
+                        for (int j = 0; j < 4; ++j)
+                            st[lane * 4 + (j ^ wsw)] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        __syncwarp();
+                        if (p.vec_ok && col + 4 <= p.Cout) {
+                            float4 x[4], rr[4];
+                            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                            // issue every global read of the unit before the first use
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g8 + i]) * p.scale;
-                                const int col = col0 + g8;
-                                if (p.bias) {
-                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                                    x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-                                    x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-                                }
-                                if (bn_row) {
-                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bn_row + col));
-                                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bn_row + col + 4));
-                                    x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-                                    x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-                                }
-                                if (p.res) {
-                                    if (p.res_f32) {
-                                        const float* r = reinterpret_cast<const float*>(p.res) + off + col;
-                                        const float4 r0 = *reinterpret_cast<const float4*>(r);
-                                        const float4 r1 = *reinterpret_cast<const float4*>(r + 4);
-                                        x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
-                                        x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
-                                    } else {
-                                        const uint4 r = *reinterpret_cast<const uint4*>(
-                                            reinterpret_cast<const __nv_bfloat16*>(p.res) + off + col);
-                                        float2 f;
-                                        f = unpack_bf16x2(r.x); x[0] += f.x; x[1] += f.y;
-                                        f = unpack_bf16x2(r.y); x[2] += f.x; x[3] += f.y;
-                                        f = unpack_bf16x2(r.z); x[4] += f.x; x[5] += f.y;
-                                        f = unpack_bf16x2(r.w); x[6] += f.x; x[7] += f.y;
+                            for (int i = 0; i < 4; ++i) {
+                                rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (g.valid >> i & 1) {
+                                    if (p.res) {
+                                        if (p.res_f32) {
+                                            rr[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + g.off[i] + col);
+                                        } else {
+                                            const uint2 r2 = *reinterpret_cast<const uint2*>(
+                                                reinterpret_cast<const __nv_bfloat16*>(p.res) + g.off[i] + col);
+                                            const float2 f0 = unpack_bf16x2(r2.x), f1 = unpack_bf16x2(r2.y);
+                                            rr[i] = make_float4(f0.x, f0.y, f1.x, f1.y);
+                                        }
+                                    }
+                                    if (p.bias_n) {
+                                        const float4 bn = __ldg(reinterpret_cast<const float4*>(p.bias_n + (long long)g.n[i] * p.bias_n_ld + col));
+                                        rr[i].x += bn.x; rr[i].y += bn.y; rr[i].z += bn.z; rr[i].w += bn.w;
                                     }
                                 }
-                                if (p.act == 1) {
+                            }
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i) x[i] = silu_f(x[i]);
-                                }
-                                if (p.out_f32) {
-                                    float* o = p.out_f32 + off + col;
-                                    *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
-                                    *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
-                                }
-                                if (p.out_bf16) {
-                                    *reinterpret_cast<uint4*>(p.out_bf16 + off + col) =
-                                        make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),
-                                                   pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+                            for (int i = 0; i < 4; ++i) {
+                                const int r = rsub + 8 * i;
+                                x[i] = st[r * 4 + (quad ^ ((r >> 1) & 3))];
+                            }
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                if (g.valid >> i & 1) {
+                                    float y0 = x[i].x * p.scale + b.x + rr[i].x, y1 = x[i].y * p.scale + b.y + rr[i].y;
+                                    float y2 = x[i].z * p.scale + b.z + rr[i].z, y3 = x[i].w * p.scale + b.w + rr[i].w;
+                                    if (p.act == 1) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+                                    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + g.off[i] + col) = make_float4(y0, y1, y2, y3);
+                                    if (p.out_bf16)
+                                        *reinterpret_cast<uint2*>(p.out_bf16 + g.off[i] + col) =
+                                            make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
                                 }
                             }
                         } else {
-                            // ragged tail / unaligned output: scalar path (fully unrolled so v[] stays in registers)
+                            // ragged tail / unaligned output: scalar path
 #pragma unroll
-                            for (int i = 0; i < CH; ++i) {
-                                const int col = col0 + i;
-                                if (col < p.Cout) {
-                                    float x = __uint_as_float(v[i]) * p.scale;
-                                    if (p.bias) x += __ldg(p.bias + col);
-                                    if (bn_row) x += __ldg(bn_row + col);
-                                    if (p.res) {
-                                        x += p.res_f32 ? reinterpret_cast<const float*>(p.res)[off + col]
-                                                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[off + col]);
+                            for (int i = 0; i < 4; ++i) {
+                                const int r = rsub + 8 * i;
+                                const float4 xv = st[r * 4 + (quad ^ ((r >> 1) & 3))];
+                                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                                if (g.valid >> i & 1) {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const int cidx = col + e;
+                                        if (cidx < p.Cout) {
+                                            float y = xs[e] * p.scale;
+                                            if (p.bias) y += __ldg(p.bias + cidx);
+                                            if (p.bias_n) y += __ldg(p.bias_n + (long long)g.n[i] * p.bias_n_ld + cidx);
+                                            if (p.res) {
+                                                y += p.res_f32 ? reinterpret_cast<const float*>(p.res)[g.off[i] + cidx]
+                                                               : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[g.off[i] + cidx]);
+                                            }
+                                            y = apply_act(y, p.act);
+                                            if (p.out_f32) p.out_f32[g.off[i] + cidx] = y;
+                                            if (p.out_bf16) p.out_bf16[g.off[i] + cidx] = __float2bfloat16(y);
+                                        }
                                     }
-                                    x = apply_act(x, p.act);
-                                    if (p.out_f32) p.out_f32[off + col] = x;
-                                    if (p.out_bf16) p.out_bf16[off + col] = __float2bfloat16(x);
                                 }
                             }
                         }
                     }
                 }
+                // this warp is done with the slot: one arrival per warp on the LEADER's barrier
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty_leader + slot * 8);
             }
-            tc_fence_before();
-            mbar_arrive(&acc_empty_bar[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    cluster_sync_all();                 // the peer may still be reading this CTA's shared memory / signalling its barriers
+    if (warp == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ============================================================================================ host side
@@ -312,19 +382,30 @@ static int encode_act_map(CUtensorMap* m, const void* base, int C, long long W, 
                              CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BN>
-static int launch_gemm(const GemmParams& gp, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+template <int BNC, int NC>
+static int launch_gemm(GemmParams& gp, const void* w, long long ktot, long long w_ld, cudaStream_t stream) {
+    using Cfg = GemmCfg<BNC, NC>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BNC, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_gemm_kernel)");
         attr_done = true;
     }
-    const int total = gp.n_tiles_m * gp.n_tiles_n;
-    const int grid = total < sm_count() ? total : sm_count();
-    conv_gemm_kernel<BN><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(gp);
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)gp.Cout};
+        cuuint64_t strides[1] = {(cuuint64_t)w_ld * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)(BNC / 2)};
+        cuuint32_t estr[2] = {1, 1};
+        int rc = encode_tensor_map(&gp.bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    gp.n_tiles_n = (gp.Cout + Cfg::N_TILE - 1) / Cfg::N_TILE;
+    const int total = gp.n_pairs_m * gp.n_tiles_n;
+    const int max_clusters = sm_count() / 2;
+    const int clusters = total < max_clusters ? total : max_clusters;
+    conv_gemm_kernel<BNC, NC><<<2 * clusters, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(gp);
     count_launch();
     return check_launch("conv_gemm_kernel");
 }
@@ -359,7 +440,8 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
     gp.tiles_w = (OW + TW - 1) / TW;
     gp.tiles_h = (OH + TH - 1) / TH;
     gp.tiles_n = (N + TN - 1) / TN;
-    gp.n_tiles_m = gp.tiles_w * gp.tiles_h * gp.tiles_n;
+    const int n_tiles_m = gp.tiles_w * gp.tiles_h * gp.tiles_n;
+    gp.n_pairs_m = (n_tiles_m + 1) / 2;          // an odd last 128-pixel tile is paired with an all-padding one
     gp.N = N; gp.OH = OH; gp.OW = OW; gp.Cout = c->Cout;
 
     const int cblk = (c->x.C + 63) / 64;
@@ -407,31 +489,9 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
     gp.n_items = n_items;
     gp.total_kblk = (ktot + 63) / 64;
 
-    // tile width in N
-    int BN;
-    if (c->act == RG_ACT_GEGLU) {
-        if (c->Cout % 160 != 0 || !c->out_bf16 || c->out_f32 || c->res || c->bias_n)
-            return set_error(RG_ERR_ARG, "rg_conv2d: GEGLU needs Cout % 160 == 0 and a bf16 output only");
-        BN = 160;
-    } else if (c->Cout <= 16) BN = 16;
-    else if (c->Cout <= 32) BN = 32;
-    else if (c->Cout <= 64) BN = 64;
-    else if (c->Cout % 160 == 0) BN = 160;
-    else BN = 128;
-    gp.n_tiles_n = (c->Cout + BN - 1) / BN;
-
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)c->Cout};
-        const long long w_ld = c->w_ld ? c->w_ld : ktot;
-        if (w_ld % 8 || w_ld < ktot) return set_error(RG_ERR_ARG, "rg_conv2d: w_ld must be a multiple of 8 and >= Ktot");
-        cuuint64_t strides[1] = {(cuuint64_t)w_ld * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)BN};
-        cuuint32_t estr[2] = {1, 1};
-        if (reinterpret_cast<uintptr_t>(c->w) & 15) return set_error(RG_ERR_ARG, "rg_conv2d: weights must be 16-B aligned");
-        rc = encode_tensor_map(&gp.bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->w, dims, strides, box, estr,
-                               CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc) return rc;
-    }
+    const long long w_ld = c->w_ld ? c->w_ld : ktot;
+    if (w_ld % 8 || w_ld < ktot) return set_error(RG_ERR_ARG, "rg_conv2d: w_ld must be a multiple of 8 and >= Ktot");
+    if (reinterpret_cast<uintptr_t>(c->w) & 15) return set_error(RG_ERR_ARG, "rg_conv2d: weights must be 16-B aligned");
 
     gp.bias = c->bias; gp.bias_n = c->bias_n; gp.bias_n_ld = c->bias_n_ld;
     gp.res = c->res; gp.res_f32 = c->res_dtype == RG_DT_F32;
@@ -444,13 +504,24 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
                          !(reinterpret_cast<uintptr_t>(c->res) & 15) && !(reinterpret_cast<uintptr_t>(c->bias) & 15) &&
                          !(reinterpret_cast<uintptr_t>(c->bias_n) & 15) && (c->bias_n_ld % 4 == 0) && (c->Cout % 4 == 0);
     gp.vec_ok = aligned ? 1 : 0;
-    if (c->act == RG_ACT_GEGLU && !aligned) return set_error(RG_ERR_ARG, "rg_conv2d: GEGLU output must be 16-B aligned");
 
-    switch (BN) {
-        case 16: return launch_gemm<16>(gp, stream);
-        case 32: return launch_gemm<32>(gp, stream);
-        case 64: return launch_gemm<64>(gp, stream);
-        case 128: return launch_gemm<128>(gp, stream);
-        default: return launch_gemm<160>(gp, stream);
+    // ---- tile shape.  Columns: one or two chunks of BNC.  The 2 x 160 tile halves the L2 traffic per FLOP but
+    // quantises the grid more coarsely; estimate both (cycles per k-block: max(MMA, L2 fill at ~43 B/clk/SM)).
+    const int Cout = c->Cout;
+    if (c->act == RG_ACT_GEGLU) {
+        if (Cout % 32 != 0 || !c->out_bf16 || c->out_f32 || c->res || c->bias_n || !aligned)
+            return set_error(RG_ERR_ARG, "rg_conv2d: GEGLU needs Cout % 32 == 0 and a 16-B aligned bf16 output only");
     }
+    const int clusters = sm_count() / 2;
+    auto waves = [&](int n_tile) { return (int)(((long long)gp.n_pairs_m * ((Cout + n_tile - 1) / n_tile) + clusters - 1) / clusters); };
+    if (Cout % 160 == 0) {
+        // short K: the epilogue dominates and wants the full double buffering of the 1 x 160 tile (3 TMEM slots)
+        if (Cout % 320 == 0 && gp.total_kblk > 24 && (long long)waves(320) * 865 <= (long long)waves(160) * 625)
+            return launch_gemm<160, 2>(gp, c->w, ktot, w_ld, stream);
+        return launch_gemm<160, 1>(gp, c->w, ktot, w_ld, stream);
+    }
+    if (Cout > 128) return launch_gemm<256, 1>(gp, c->w, ktot, w_ld, stream);
+    if (Cout > 64) return launch_gemm<128, 1>(gp, c->w, ktot, w_ld, stream);
+    if (Cout > 32) return launch_gemm<64, 1>(gp, c->w, ktot, w_ld, stream);
+    return launch_gemm<32, 1>(gp, c->w, ktot, w_ld, stream);
 }

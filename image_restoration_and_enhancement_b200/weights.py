@@ -11,7 +11,7 @@ from collections import OrderedDict
 
 import torch
 
-GEGLU_TILE = 160          # N tile of the GEMM kernel's GEGLU epilogue: 80 value columns | 80 gate columns
+GEGLU_TILE = 32           # unit of the GEMM kernel's GEGLU epilogue: 16 value columns | their 16 gate columns
 
 
 # ------------------------------------------------------------------------------------------------ packing
@@ -22,7 +22,7 @@ def pack_conv(w: torch.Tensor) -> torch.Tensor:
 
 def interleave_geglu(w: torch.Tensor, b: torch.Tensor | None):
     """Reorder the rows of GEGLU's projection ([2*D, K]: D value rows then D gate rows) so that every
-    160-row tile holds 80 value rows followed by their 80 gate rows."""
+    32-row unit holds 16 value rows followed by their 16 gate rows."""
     D = w.shape[0] // 2
     half = GEGLU_TILE // 2
     assert D % half == 0

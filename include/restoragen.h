@@ -40,7 +40,7 @@ typedef void* rg_stream_t; /* cudaStream_t */
 
 #define RG_ACT_NONE 0
 #define RG_ACT_SILU 1
-#define RG_ACT_GEGLU 2          /* columns interleaved a|g per 160-wide tile; output width = Cout/2 */
+#define RG_ACT_GEGLU 2          /* columns interleaved 16 value | 16 gate per 32-wide unit; output width = Cout/2 */
 
 #define RG_DT_BF16 0
 #define RG_DT_F32 1

@@ -68,7 +68,7 @@ def case_linear(M=256, K=128, N=160, bias=True, res=None, act=RG_ACT_NONE, f32_o
 
 
 def case_geglu(M=300, K=320, C4=1280, seed=5):
-    """ff.net.0 (GEGLU): proj -> chunk(2) -> a * gelu(g); weight rows interleaved per 160-wide tile on the host."""
+    """ff.net.0 (GEGLU): proj -> chunk(2) -> a * gelu(g); weight rows interleaved per 32-wide unit on the host."""
     _setup()
     from image_restoration_and_enhancement_b200.weights import interleave_geglu
     x = _rand((M, K), seed)
