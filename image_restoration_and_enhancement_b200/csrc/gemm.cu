@@ -22,6 +22,7 @@
 //   warp instruction touches 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes), fusing scale, bias,
 //   per-image bias (time embedding), residual add (bf16 or fp32), SiLU, GEGLU (a * gelu(g)) and the bf16 and/or
 //   fp32 stores with arbitrary output pixel strides.
+#include <stdlib.h>
 #include "common.cuh"
 #include "internal.h"
 
@@ -50,6 +51,14 @@ struct GemmParams {
     int act;
     float scale;
     int vec_ok;
+    // TMA epilogue (epi_tma != 0): per-warp boxes of {16 columns, 32 pixels}
+    int epi_tma;
+    int prim_f32;                     // dtype of the primary staging buffer (residual in / same-dtype output in place)
+    int prim_store;                   // an output of the primary dtype exists
+    int sec_store;                    // bf16 output next to an fp32 primary buffer
+    int dbg;                          // RG_GEMM_DEBUG bits (perf experiments only): 1 skip units, 2 skip stores, 4 skip residual
+    int out_cols;                     // Cout, or Cout / 2 for GEGLU
+    CUtensorMap resmap, pmap, hmap;   // residual load, primary store, secondary (bf16) store
 };
 
 constexpr int kGemmThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
@@ -62,17 +71,23 @@ struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_CHUNK_BYTES = (BNC / 2) * BK * 2;  // this CTA's half of one chunk
     static constexpr int STAGE_BYTES = A_BYTES + NC * B_CHUNK_BYTES;
-    static constexpr int STAGING_BYTES = kEpiWarps * 2 * 2048;  // per warp: two [32 rows][16 fp32] transpose buffers
+    // per epilogue warp: NBUF primary buffers [32 rows][16 fp32] (residual in, result in place, TMA store out) and
+    // HBUF secondary buffers [32 rows][16 bf16]; the direct (non-TMA) path uses the first two primaries to transpose
+    static constexpr int NBUF = NC == 1 ? 3 : 2;
+    static constexpr int HBUF = NC == 1 ? 2 : 1;
+    static constexpr int WARP_STAGING = NBUF * 2048 + HBUF * 1024;
+    static constexpr int STAGING_BYTES = kEpiWarps * WARP_STAGING;
     static constexpr int BAR_BYTES = 512;
     static constexpr int MAX_STAGES = (227 * 1024 - 1024 - STAGING_BYTES - BAR_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+    static_assert(STAGES >= 4, "pipeline too shallow");
     static constexpr int SLOTS = 512 / BNC > 4 ? 4 : 512 / BNC;
     static constexpr int TMEM_COLS = SLOTS * BNC <= 32 ? 32 : SLOTS * BNC <= 64 ? 64 : SLOTS * BNC <= 128 ? 128
                                    : SLOTS * BNC <= 256 ? 256 : 512;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;
     static_assert(BNC % 32 == 0 && BNC >= 32 && BNC <= 256, "BNC");
     static_assert(SLOTS >= NC + (NC > 1 ? 1 : 1), "TMEM ring too small");
-    static_assert((2 * STAGES + 2 * SLOTS) * 8 + 8 <= BAR_BYTES, "barrier area");
+    static_assert((2 * STAGES + 2 * SLOTS + kEpiWarps * NBUF) * 8 + 8 <= BAR_BYTES, "barrier area");
     static_assert(B_CHUNK_BYTES % 1024 == 0, "operand tiles must stay 1024-B aligned");
 };
 
@@ -84,6 +99,182 @@ struct RowGeom {
     int n[4];
     unsigned valid;        // bit i: read-phase row i is a real output pixel
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA epilogue.  Every epilogue warp owns 32 accumulator rows (its TMEM lane quarter) and walks its share of the
+// tile's 16-column units.  Per unit: the residual box {16 cols, 32 pixels} was prefetched by TMA into the warp's
+// primary buffer one unit (or more) ahead; the accumulator comes from TMEM with one tcgen05.ld; thread r combines
+// row r in shared memory IN PLACE (scale, bias, per-image bias, residual, activation) and the warp's lane 0 hands the
+// finished box to a TMA store.  No global load or store is issued by the math threads, nothing waits for a memory
+// round trip, every byte moves in full 32/64-byte row segments, and ragged tile edges are clipped by the tensor map.
+// Requires Cout % N_TILE == 0 (every unit of every chunk is real), which holds for all UNet / VAE body layers.
+template <int BNC, int NC>
+__device__ __forceinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging, uint64_t* acc_full, uint64_t* acc_empty,
+                                             uint64_t* res_bar_all, uint32_t tmem_base, uint32_t rank, int cluster_id,
+                                             int n_clusters, int warp, int lane) {
+    using Cfg = GemmCfg<BNC, NC>;
+    constexpr int NBUF = Cfg::NBUF, HBUF = Cfg::HBUF;
+    const int ew = warp - 2;
+    const int q = warp & 3, half = ew >> 2;
+    // everything the unit loop needs, in registers
+    const bool geglu = p.act == 2, silu = p.act == 1;
+    const bool prim_f32 = p.prim_f32 != 0, prim_store = p.prim_store != 0, sec_store = p.sec_store != 0;
+    const bool has_res = p.res != nullptr && !(p.dbg & 4);
+    const bool skip_units = (p.dbg & 1) != 0, skip_store = (p.dbg & 2) != 0;
+    const float scale = p.scale;
+    const float* const bias = p.bias;
+    const int gsh = geglu ? 1 : 0;                        // output column = GEMM column >> gsh
+    const int UW = geglu ? 32 : 16;                       // accumulator columns per unit
+    const int UPC = BNC / UW;                             // units per chunk
+    const int CNT = (UPC - half + 1) / 2;                 // units per chunk handled by this warp (u = half, half+2, ..)
+    uint8_t* const pbuf0 = staging + ew * Cfg::WARP_STAGING;
+    uint8_t* const hbuf0 = pbuf0 + NBUF * 2048;
+    uint64_t* const res_bar = res_bar_all + ew * NBUF;
+    const uint32_t acc_empty_leader = mapa_shared(smem_u32(acc_empty), 0);
+    const int total_tiles = p.n_pairs_m * p.n_tiles_n;
+    const int TW = 1 << p.lw, TH = 1 << p.lh, lwh = p.lw + p.lh, TN = 128 >> lwh;
+    const int row0 = q * 32;
+    const int res_bytes = prim_f32 ? 2048 : 1024;
+    const int sw = (lane >> 1) & 3;                       // SWIZZLE_64B phase of this lane's 64-byte fp32 row
+    const int fo = lane * 64, ho = lane * 32;
+
+    // box origin (w, h, n) of this warp's 32 rows in tile `tile`
+    auto box_origin = [&](int tile, int& cw, int& ch, int& cn, int& n_tile, int& tni) {
+        const int mp = tile / p.n_tiles_n;
+        n_tile = tile - mp * p.n_tiles_n;
+        const int m_tile = 2 * mp + (int)rank;
+        const int twi = m_tile % p.tiles_w;
+        const int rest = m_tile / p.tiles_w;
+        const int thi = rest % p.tiles_h;
+        tni = rest / p.tiles_h;
+        cw = twi * TW + (row0 & (TW - 1));
+        ch = thi * TH + ((row0 >> p.lw) & (TH - 1));
+        cn = tni * TN + (row0 >> lwh);
+    };
+
+    uint32_t A = 0;                                       // units processed so far by this warp
+    uint32_t cc = 0;
+    int cw = 0, ch = 0, cn = 0, n_tile = 0, tni = 0;
+    if (cluster_id < total_tiles) box_origin(cluster_id, cw, ch, cn, n_tile, tni);
+    if (has_res && lane == 0 && CNT > 0 && cluster_id < total_tiles && !skip_units) {      // very first residual box
+        mbar_expect_tx(&res_bar[0], res_bytes);
+        tma_load_4d(pbuf0, &p.resmap, &res_bar[0], (n_tile * Cfg::N_TILE + half * UW) >> gsh, cw, ch, cn);
+    }
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, cc += NC) {
+        // next tile's origin: target of the residual prefetch issued from this tile's last unit
+        const bool has_next = tile + n_clusters < total_tiles;
+        int cw2 = 0, ch2 = 0, cn2 = 0, n_tile2 = 0, tni2 = 0;
+        if (has_next) box_origin(tile + n_clusters, cw2, ch2, cn2, n_tile2, tni2);
+        int n_row = tni * TN + ((row0 + lane) >> lwh);
+        if (n_row >= p.N) n_row = p.N - 1;                // padding rows: any valid image (their result is clipped)
+        const float* const bn_row = p.bias_n ? p.bias_n + (long long)n_row * p.bias_n_ld : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < NC; ++c) {
+            const uint32_t slot = (cc + c) % Cfg::SLOTS, use = (cc + c) / Cfg::SLOTS;
+            mbar_wait(&acc_full[slot], use & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)row0 << 16) + slot * BNC;
+            const int gcol0 = n_tile * Cfg::N_TILE + c * BNC;
+#pragma unroll 1
+            for (int k = 0; k < CNT && !skip_units; ++k, ++A) {
+                const int u = half + 2 * k;
+                const int gcol = gcol0 + u * UW;                               // GEMM column (bias index)
+                const int ocol = gcol >> gsh;                                  // output column
+                const int buf = A % NBUF;
+                uint8_t* const pb = pbuf0 + buf * 2048;
+                uint8_t* const hb = hbuf0 + (A % HBUF) * 1024;
+                // ---- lane 0: the buffers about to be refilled are no longer read by an earlier store; prefetch the
+                //      next unit's residual
+                if (lane == 0) {
+                    bulk_wait_read<NBUF - 2>();
+                    if (has_res) {
+                        const int nb = (A + 1) % NBUF;
+                        if (k + 1 < CNT) {
+                            mbar_expect_tx(&res_bar[nb], res_bytes);
+                            tma_load_4d(pbuf0 + nb * 2048, &p.resmap, &res_bar[nb], (gcol + 2 * UW) >> gsh, cw, ch, cn);
+                        } else if (c + 1 < NC) {
+                            mbar_expect_tx(&res_bar[nb], res_bytes);
+                            tma_load_4d(pbuf0 + nb * 2048, &p.resmap, &res_bar[nb], (gcol0 + BNC + half * UW) >> gsh, cw, ch, cn);
+                        } else if (has_next) {
+                            mbar_expect_tx(&res_bar[nb], res_bytes);
+                            tma_load_4d(pbuf0 + nb * 2048, &p.resmap, &res_bar[nb], (n_tile2 * Cfg::N_TILE + half * UW) >> gsh,
+                                        cw2, ch2, cn2);
+                        }
+                    }
+                }
+                __syncwarp();
+                // ---- accumulator
+                uint32_t va[16];
+                tmem_ld16(taddr + u * UW, va);
+                if (geglu) {
+                    uint32_t vg[16];
+                    tmem_ld16(taddr + u * UW + 16, vg);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+                        if (bias) {
+                            ba = __ldg(reinterpret_cast<const float4*>(bias + gcol + 4 * j));
+                            bg = __ldg(reinterpret_cast<const float4*>(bias + gcol + 16 + 4 * j));
+                        }
+                        const float y0 = fmaf(__uint_as_float(va[4 * j]), scale, ba.x) * gelu_fast_f(fmaf(__uint_as_float(vg[4 * j]), scale, bg.x));
+                        const float y1 = fmaf(__uint_as_float(va[4 * j + 1]), scale, ba.y) * gelu_fast_f(fmaf(__uint_as_float(vg[4 * j + 1]), scale, bg.y));
+                        const float y2 = fmaf(__uint_as_float(va[4 * j + 2]), scale, ba.z) * gelu_fast_f(fmaf(__uint_as_float(vg[4 * j + 2]), scale, bg.z));
+                        const float y3 = fmaf(__uint_as_float(va[4 * j + 3]), scale, ba.w) * gelu_fast_f(fmaf(__uint_as_float(vg[4 * j + 3]), scale, bg.w));
+                        *reinterpret_cast<uint2*>(pb + ho + j * 8) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                    }
+                } else {
+                    tmem_ld_wait();
+                    if (has_res) mbar_wait(&res_bar[buf], (A / NBUF) & 1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float y0 = __uint_as_float(va[4 * j]) * scale, y1 = __uint_as_float(va[4 * j + 1]) * scale;
+                        float y2 = __uint_as_float(va[4 * j + 2]) * scale, y3 = __uint_as_float(va[4 * j + 3]) * scale;
+                        if (bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + gcol + 4 * j));
+                            y0 += b.x; y1 += b.y; y2 += b.z; y3 += b.w;
+                        }
+                        if (bn_row) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bn_row + gcol + 4 * j));
+                            y0 += b.x; y1 += b.y; y2 += b.z; y3 += b.w;
+                        }
+                        if (prim_f32) {
+                            float4* const slot4 = reinterpret_cast<float4*>(pb + fo + ((j ^ sw) << 4));
+                            if (has_res) { const float4 r = *slot4; y0 += r.x; y1 += r.y; y2 += r.z; y3 += r.w; }
+                            if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+                            if (prim_store) *slot4 = make_float4(y0, y1, y2, y3);
+                            if (sec_store) *reinterpret_cast<uint2*>(hb + ho + j * 8) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                        } else {
+                            uint2* const slot2 = reinterpret_cast<uint2*>(pb + ho + j * 8);
+                            if (has_res) {
+                                const uint2 r = *slot2;
+                                const float2 f0 = unpack_bf16x2(r.x), f1 = unpack_bf16x2(r.y);
+                                y0 += f0.x; y1 += f0.y; y2 += f1.x; y3 += f1.y;
+                            }
+                            if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+                            *slot2 = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                        }
+                    }
+                }
+                // ---- hand the finished box(es) to the TMA engine
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && !skip_store) {
+                    if (prim_store) tma_store_4d(&p.pmap, pb, ocol, cw, ch, cn);
+                    if (sec_store) tma_store_4d(&p.hmap, hb, ocol, cw, ch, cn);
+                    bulk_commit();
+                }
+            }
+            // this warp is done with the slot: one arrival per warp on the LEADER's barrier
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty_leader + slot * 8);
+        }
+        cw = cw2; ch = ch2; cn = cn2; n_tile = n_tile2; tni = tni2;
+    }
+    if (lane == 0) bulk_wait_all();                       // every store has landed before the CTA may exit
+    __syncwarp();
+}
 
 template <int BNC, int NC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
@@ -97,7 +288,8 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     uint64_t* empty_bar = full_bar + Cfg::STAGES;
     uint64_t* acc_full = empty_bar + Cfg::STAGES;
     uint64_t* acc_empty = acc_full + Cfg::SLOTS;                                       // leader's are the live ones
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + Cfg::SLOTS);
+    uint64_t* res_bar = acc_empty + Cfg::SLOTS;                                        // [epilogue warp][NBUF]
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps * Cfg::NBUF);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -107,10 +299,12 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 5; ++i) tma_prefetch_desc(&p.amap[i]);
         tma_prefetch_desc(&p.bmap);
+        if (p.epi_tma) { tma_prefetch_desc(&p.resmap); tma_prefetch_desc(&p.pmap); tma_prefetch_desc(&p.hmap); }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < Cfg::SLOTS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * kEpiWarps); }
+        for (int s = 0; s < kEpiWarps * Cfg::NBUF; ++s) mbar_init(&res_bar[s], 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_pair(tmem_base_smem, Cfg::TMEM_COLS);
@@ -190,176 +384,180 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         }
     } else {
         // ===================================================================== epilogue (both CTAs, own 128 rows)
-        const int q = warp & 3;                    // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;          // units are dealt alternately to the two warps of a quarter
-        const int rsub = lane >> 2, quad = lane & 3;
-        float4* st0 = reinterpret_cast<float4*>(staging + (warp - 2) * 4096);
-        float4* st1 = st0 + 128;
-        const int wsw = (lane >> 1) & 3;           // write-phase swizzle of this lane's row
-        const bool geglu = p.act == 2;
-        const uint32_t acc_empty_leader = mapa_shared(smem_u32(acc_empty), 0);
-        uint32_t cc = 0;
-        for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, cc += NC) {
-            const int mp = tile / p.n_tiles_n, n_tile = tile - mp * p.n_tiles_n;
-            const int m_tile = 2 * mp + (int)rank;
-            const int twi = m_tile % p.tiles_w;
-            const int rest = m_tile / p.tiles_w;
-            const int thi = rest % p.tiles_h, tni = rest / p.tiles_h;
-            // geometry of this lane's own row (TMEM lane q*32 + lane), then of the 4 rows it handles after the transpose
-            RowGeom g;
-            {
-                const int row = q * 32 + lane;
-                const int ow = twi * TW + (row & (TW - 1));
-                const int oh = thi * TH + ((row >> p.lw) & (TH - 1));
-                const int n = tni * (128 >> (p.lw + p.lh)) + (row >> (p.lw + p.lh));
-                const bool valid = (ow < p.OW) && (oh < p.OH) && (n < p.N);
-                const long long off = valid ? ((long long)n * p.osn + (long long)oh * p.osh + (long long)ow * p.osw) : 0;
-                g.valid = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int src = rsub + 8 * i;
-                    g.off[i] = __shfl_sync(0xffffffffu, off, src);
-                    g.n[i] = __shfl_sync(0xffffffffu, n, src);
-                    g.valid |= (__shfl_sync(0xffffffffu, (int)valid, src) ? 1u : 0u) << i;
-                }
-            }
-#pragma unroll 1
-            for (int c = 0; c < NC; ++c) {
-                const uint32_t slot = (cc + c) % Cfg::SLOTS, use = (cc + c) / Cfg::SLOTS;
-                mbar_wait(&acc_full[slot], use & 1);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * BNC;
-                const int ncol0 = n_tile * Cfg::N_TILE + c * BNC;          // first weight row / GEMM column of this chunk
-                if (geglu) {
-                    // unit = 16 value columns followed by their 16 gate columns (host interleave, weights.interleave_geglu)
-#pragma unroll 1
-                    for (int u = half; u < BNC / 32; u += 2) {
-                        if (ncol0 + u * 32 >= p.Cout) break;             // warp-uniform: the rest of the chunk is padding
-                        uint32_t va[16], vg[16];
-                        tmem_ld16(taddr + u * 32, va);
-                        tmem_ld16(taddr + u * 32 + 16, vg);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            st0[lane * 4 + (j ^ wsw)] = make_float4(__uint_as_float(va[4 * j]), __uint_as_float(va[4 * j + 1]),
-                                                                    __uint_as_float(va[4 * j + 2]), __uint_as_float(va[4 * j + 3]));
-                            st1[lane * 4 + (j ^ wsw)] = make_float4(__uint_as_float(vg[4 * j]), __uint_as_float(vg[4 * j + 1]),
-                                                                    __uint_as_float(vg[4 * j + 2]), __uint_as_float(vg[4 * j + 3]));
-                        }
-                        __syncwarp();
-                        const int ca = ncol0 + u * 32 + quad * 4, cg = ca + 16;
-                        const int co = (ncol0 >> 1) + u * 16 + quad * 4;
-                        float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
-                        if (p.bias) {
-                            ba = __ldg(reinterpret_cast<const float4*>(p.bias + ca));
-                            bg = __ldg(reinterpret_cast<const float4*>(p.bias + cg));
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int r = rsub + 8 * i;
-                            const float4 a = st0[r * 4 + (quad ^ ((r >> 1) & 3))];
-                            const float4 gt = st1[r * 4 + (quad ^ ((r >> 1) & 3))];
-                            if (g.valid >> i & 1) {
-                                const float y0 = (a.x * p.scale + ba.x) * gelu_erf_f(gt.x * p.scale + bg.x);
-                                const float y1 = (a.y * p.scale + ba.y) * gelu_erf_f(gt.y * p.scale + bg.y);
-                                const float y2 = (a.z * p.scale + ba.z) * gelu_erf_f(gt.z * p.scale + bg.z);
-                                const float y3 = (a.w * p.scale + ba.w) * gelu_erf_f(gt.w * p.scale + bg.w);
-                                *reinterpret_cast<uint2*>(p.out_bf16 + g.off[i] + co) =
-                                    make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
-                            }
-                        }
-                        __syncwarp();
+        if (p.epi_tma) {
+            epilogue_tma<BNC, NC>(p, staging, acc_full, acc_empty, res_bar, tmem_base, rank, cluster_id, n_clusters, warp, lane);
+        } else {
+            const int q = warp & 3;                    // TMEM lane quarter this warp may access
+            const int half = (warp - 2) >> 2;          // units are dealt alternately to the two warps of a quarter
+            const int rsub = lane >> 2, quad = lane & 3;
+            float4* st0 = reinterpret_cast<float4*>(staging + (warp - 2) * Cfg::WARP_STAGING);
+            float4* st1 = st0 + 128;
+            const int wsw = (lane >> 1) & 3;           // write-phase swizzle of this lane's row
+            const bool geglu = p.act == 2;
+            const uint32_t acc_empty_leader = mapa_shared(smem_u32(acc_empty), 0);
+            uint32_t cc = 0;
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, cc += NC) {
+                const int mp = tile / p.n_tiles_n, n_tile = tile - mp * p.n_tiles_n;
+                const int m_tile = 2 * mp + (int)rank;
+                const int twi = m_tile % p.tiles_w;
+                const int rest = m_tile / p.tiles_w;
+                const int thi = rest % p.tiles_h, tni = rest / p.tiles_h;
+                // geometry of this lane's own row (TMEM lane q*32 + lane), then of the 4 rows it handles after the transpose
+                RowGeom g;
+                {
+                    const int row = q * 32 + lane;
+                    const int ow = twi * TW + (row & (TW - 1));
+                    const int oh = thi * TH + ((row >> p.lw) & (TH - 1));
+                    const int n = tni * (128 >> (p.lw + p.lh)) + (row >> (p.lw + p.lh));
+                    const bool valid = (ow < p.OW) && (oh < p.OH) && (n < p.N);
+                    const long long off = valid ? ((long long)n * p.osn + (long long)oh * p.osh + (long long)ow * p.osw) : 0;
+                    g.valid = 0;
+    #pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int src = rsub + 8 * i;
+                        g.off[i] = __shfl_sync(0xffffffffu, off, src);
+                        g.n[i] = __shfl_sync(0xffffffffu, n, src);
+                        g.valid |= (__shfl_sync(0xffffffffu, (int)valid, src) ? 1u : 0u) << i;
                     }
-                } else {
-                    int ub = 0;                              // staging buffer toggle: one __syncwarp per unit suffices
-#pragma unroll 1
-                    for (int u = half; u < BNC / 16; u += 2, ub ^= 1) {
-                        const int col = ncol0 + u * 16 + quad * 4;
-                        if (ncol0 + u * 16 >= p.Cout) break;             // warp-uniform: the rest of the chunk is padding
-                        uint32_t v[16];
-                        tmem_ld16(taddr + u * 16, v);
-                        tmem_ld_wait();
-                        float4* st = ub ? st1 : st0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            st[lane * 4 + (j ^ wsw)] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                        __syncwarp();
-                        if (p.vec_ok && col + 4 <= p.Cout) {
-                            float4 x[4], rr[4];
-                            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                            // issue every global read of the unit before the first use
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (g.valid >> i & 1) {
-                                    if (p.res) {
-                                        if (p.res_f32) {
-                                            rr[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + g.off[i] + col);
-                                        } else {
-                                            const uint2 r2 = *reinterpret_cast<const uint2*>(
-                                                reinterpret_cast<const __nv_bfloat16*>(p.res) + g.off[i] + col);
-                                            const float2 f0 = unpack_bf16x2(r2.x), f1 = unpack_bf16x2(r2.y);
-                                            rr[i] = make_float4(f0.x, f0.y, f1.x, f1.y);
-                                        }
-                                    }
-                                    if (p.bias_n) {
-                                        const float4 bn = __ldg(reinterpret_cast<const float4*>(p.bias_n + (long long)g.n[i] * p.bias_n_ld + col));
-                                        rr[i].x += bn.x; rr[i].y += bn.y; rr[i].z += bn.z; rr[i].w += bn.w;
-                                    }
-                                }
+                }
+    #pragma unroll 1
+                for (int c = 0; c < NC; ++c) {
+                    const uint32_t slot = (cc + c) % Cfg::SLOTS, use = (cc + c) / Cfg::SLOTS;
+                    mbar_wait(&acc_full[slot], use & 1);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * BNC;
+                    const int ncol0 = n_tile * Cfg::N_TILE + c * BNC;          // first weight row / GEMM column of this chunk
+                    if (geglu) {
+                        // unit = 16 value columns followed by their 16 gate columns (host interleave, weights.interleave_geglu)
+    #pragma unroll 1
+                        for (int u = half; u < BNC / 32; u += 2) {
+                            if (ncol0 + u * 32 >= p.Cout) break;             // warp-uniform: the rest of the chunk is padding
+                            uint32_t va[16], vg[16];
+                            tmem_ld16(taddr + u * 32, va);
+                            tmem_ld16(taddr + u * 32 + 16, vg);
+                            tmem_ld_wait();
+    #pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                st0[lane * 4 + (j ^ wsw)] = make_float4(__uint_as_float(va[4 * j]), __uint_as_float(va[4 * j + 1]),
+                                                                        __uint_as_float(va[4 * j + 2]), __uint_as_float(va[4 * j + 3]));
+                                st1[lane * 4 + (j ^ wsw)] = make_float4(__uint_as_float(vg[4 * j]), __uint_as_float(vg[4 * j + 1]),
+                                                                        __uint_as_float(vg[4 * j + 2]), __uint_as_float(vg[4 * j + 3]));
                             }
-#pragma unroll
+                            __syncwarp();
+                            const int ca = ncol0 + u * 32 + quad * 4, cg = ca + 16;
+                            const int co = (ncol0 >> 1) + u * 16 + quad * 4;
+                            float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+                            if (p.bias) {
+                                ba = __ldg(reinterpret_cast<const float4*>(p.bias + ca));
+                                bg = __ldg(reinterpret_cast<const float4*>(p.bias + cg));
+                            }
+    #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const int r = rsub + 8 * i;
-                                x[i] = st[r * 4 + (quad ^ ((r >> 1) & 3))];
-                            }
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
+                                const float4 a = st0[r * 4 + (quad ^ ((r >> 1) & 3))];
+                                const float4 gt = st1[r * 4 + (quad ^ ((r >> 1) & 3))];
                                 if (g.valid >> i & 1) {
-                                    float y0 = x[i].x * p.scale + b.x + rr[i].x, y1 = x[i].y * p.scale + b.y + rr[i].y;
-                                    float y2 = x[i].z * p.scale + b.z + rr[i].z, y3 = x[i].w * p.scale + b.w + rr[i].w;
-                                    if (p.act == 1) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-                                    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + g.off[i] + col) = make_float4(y0, y1, y2, y3);
-                                    if (p.out_bf16)
-                                        *reinterpret_cast<uint2*>(p.out_bf16 + g.off[i] + col) =
-                                            make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                                    const float y0 = (a.x * p.scale + ba.x) * gelu_fast_f(gt.x * p.scale + bg.x);
+                                    const float y1 = (a.y * p.scale + ba.y) * gelu_fast_f(gt.y * p.scale + bg.y);
+                                    const float y2 = (a.z * p.scale + ba.z) * gelu_fast_f(gt.z * p.scale + bg.z);
+                                    const float y3 = (a.w * p.scale + ba.w) * gelu_fast_f(gt.w * p.scale + bg.w);
+                                    *reinterpret_cast<uint2*>(p.out_bf16 + g.off[i] + co) =
+                                        make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
                                 }
                             }
-                        } else {
-                            // ragged tail / unaligned output: scalar path
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int r = rsub + 8 * i;
-                                const float4 xv = st[r * 4 + (quad ^ ((r >> 1) & 3))];
-                                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-                                if (g.valid >> i & 1) {
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        const int cidx = col + e;
-                                        if (cidx < p.Cout) {
-                                            float y = xs[e] * p.scale;
-                                            if (p.bias) y += __ldg(p.bias + cidx);
-                                            if (p.bias_n) y += __ldg(p.bias_n + (long long)g.n[i] * p.bias_n_ld + cidx);
-                                            if (p.res) {
-                                                y += p.res_f32 ? reinterpret_cast<const float*>(p.res)[g.off[i] + cidx]
-                                                               : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[g.off[i] + cidx]);
+                            __syncwarp();
+                        }
+                    } else {
+                        int ub = 0;                              // staging buffer toggle: one __syncwarp per unit suffices
+    #pragma unroll 1
+                        for (int u = half; u < BNC / 16; u += 2, ub ^= 1) {
+                            const int col = ncol0 + u * 16 + quad * 4;
+                            if (ncol0 + u * 16 >= p.Cout) break;             // warp-uniform: the rest of the chunk is padding
+                            uint32_t v[16];
+                            tmem_ld16(taddr + u * 16, v);
+                            tmem_ld_wait();
+                            float4* st = ub ? st1 : st0;
+    #pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                st[lane * 4 + (j ^ wsw)] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                            __syncwarp();
+                            if (p.vec_ok && col + 4 <= p.Cout) {
+                                float4 x[4], rr[4];
+                                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                                // issue every global read of the unit before the first use
+    #pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (g.valid >> i & 1) {
+                                        if (p.res) {
+                                            if (p.res_f32) {
+                                                rr[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + g.off[i] + col);
+                                            } else {
+                                                const uint2 r2 = *reinterpret_cast<const uint2*>(
+                                                    reinterpret_cast<const __nv_bfloat16*>(p.res) + g.off[i] + col);
+                                                const float2 f0 = unpack_bf16x2(r2.x), f1 = unpack_bf16x2(r2.y);
+                                                rr[i] = make_float4(f0.x, f0.y, f1.x, f1.y);
                                             }
-                                            y = apply_act(y, p.act);
-                                            if (p.out_f32) p.out_f32[g.off[i] + cidx] = y;
-                                            if (p.out_bf16) p.out_bf16[g.off[i] + cidx] = __float2bfloat16(y);
+                                        }
+                                        if (p.bias_n) {
+                                            const float4 bn = __ldg(reinterpret_cast<const float4*>(p.bias_n + (long long)g.n[i] * p.bias_n_ld + col));
+                                            rr[i].x += bn.x; rr[i].y += bn.y; rr[i].z += bn.z; rr[i].w += bn.w;
+                                        }
+                                    }
+                                }
+    #pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int r = rsub + 8 * i;
+                                    x[i] = st[r * 4 + (quad ^ ((r >> 1) & 3))];
+                                }
+    #pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    if (g.valid >> i & 1) {
+                                        float y0 = x[i].x * p.scale + b.x + rr[i].x, y1 = x[i].y * p.scale + b.y + rr[i].y;
+                                        float y2 = x[i].z * p.scale + b.z + rr[i].z, y3 = x[i].w * p.scale + b.w + rr[i].w;
+                                        if (p.act == 1) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+                                        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + g.off[i] + col) = make_float4(y0, y1, y2, y3);
+                                        if (p.out_bf16)
+                                            *reinterpret_cast<uint2*>(p.out_bf16 + g.off[i] + col) =
+                                                make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                                    }
+                                }
+                            } else {
+                                // ragged tail / unaligned output: scalar path
+    #pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int r = rsub + 8 * i;
+                                    const float4 xv = st[r * 4 + (quad ^ ((r >> 1) & 3))];
+                                    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                                    if (g.valid >> i & 1) {
+    #pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            const int cidx = col + e;
+                                            if (cidx < p.Cout) {
+                                                float y = xs[e] * p.scale;
+                                                if (p.bias) y += __ldg(p.bias + cidx);
+                                                if (p.bias_n) y += __ldg(p.bias_n + (long long)g.n[i] * p.bias_n_ld + cidx);
+                                                if (p.res) {
+                                                    y += p.res_f32 ? reinterpret_cast<const float*>(p.res)[g.off[i] + cidx]
+                                                                   : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[g.off[i] + cidx]);
+                                                }
+                                                y = apply_act(y, p.act);
+                                                if (p.out_f32) p.out_f32[g.off[i] + cidx] = y;
+                                                if (p.out_bf16) p.out_bf16[g.off[i] + cidx] = __float2bfloat16(y);
+                                            }
                                         }
                                     }
                                 }
                             }
                         }
                     }
+                    // this warp is done with the slot: one arrival per warp on the LEADER's barrier
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(acc_empty_leader + slot * 8);
                 }
-                // this warp is done with the slot: one arrival per warp on the LEADER's barrier
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(acc_empty_leader + slot * 8);
             }
         }
     }
@@ -402,6 +600,7 @@ static int launch_gemm(GemmParams& gp, const void* w, long long ktot, long long 
         if (rc) return rc;
     }
     gp.n_tiles_n = (gp.Cout + Cfg::N_TILE - 1) / Cfg::N_TILE;
+    if (gp.Cout % Cfg::N_TILE != 0) gp.epi_tma = 0;        // the TMA epilogue assumes every 16-column unit is real
     const int total = gp.n_pairs_m * gp.n_tiles_n;
     const int max_clusters = sm_count() / 2;
     const int clusters = total < max_clusters ? total : max_clusters;
@@ -504,6 +703,50 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
                          !(reinterpret_cast<uintptr_t>(c->res) & 15) && !(reinterpret_cast<uintptr_t>(c->bias) & 15) &&
                          !(reinterpret_cast<uintptr_t>(c->bias_n) & 15) && (c->bias_n_ld % 4 == 0) && (c->Cout % 4 == 0);
     gp.vec_ok = aligned ? 1 : 0;
+
+    // ---- TMA epilogue: per-warp boxes of {16 columns, 32 pixels}; needs 16-byte aligned row segments and a residual
+    // of the same dtype as the buffer it is combined in (fp32 residual -> fp32 primary buffer, else the output dtype)
+    gp.out_cols = c->act == RG_ACT_GEGLU ? c->Cout / 2 : c->Cout;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("RG_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+        gp.dbg = dbg;
+    }
+    {
+        const bool res_f32 = c->res && c->res_dtype == RG_DT_F32, res_b16 = c->res && c->res_dtype == RG_DT_BF16;
+        const bool prim_f32 = c->res ? res_f32 : (c->out_f32 != nullptr);
+        const bool ok = aligned && !(res_b16 && c->out_f32) && gp.out_cols % 4 == 0 && (c->out_stride_w % 8 == 0);
+        if (ok) {
+            gp.epi_tma = 1;
+            gp.prim_f32 = prim_f32;
+            gp.prim_store = prim_f32 ? (c->out_f32 != nullptr) : 1;
+            gp.sec_store = prim_f32 && c->out_bf16 != nullptr;
+            const int bw = TW < 32 ? TW : 32;
+            const int bh = TH < 32 / bw ? TH : 32 / bw;
+            const int bn = 32 / (bw * bh);
+            auto enc = [&](CUtensorMap* m, const void* base, bool f32) -> int {
+                const long long esz = f32 ? 4 : 2;
+                // extent-1 dimensions may come with a zero / arbitrary pitch: give them a sane one
+                long long sw = c->out_stride_w, sh = c->out_stride_h, sn = c->out_stride_n;
+                if (OW == 1 && sw < gp.out_cols) sw = (gp.out_cols + 7) / 8 * 8;
+                if (OH == 1 && sh < sw * OW) sh = sw * OW;
+                if (N == 1 && sn < sh * OH) sn = sh * OH;
+                cuuint64_t dims[4] = {(cuuint64_t)gp.out_cols, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
+                cuuint64_t strides[3] = {(cuuint64_t)(sw * esz), (cuuint64_t)(sh * esz), (cuuint64_t)(sn * esz)};
+                cuuint32_t box[4] = {16, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+                cuuint32_t estr[4] = {1, 1, 1, 1};
+                return encode_tensor_map(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base,
+                                         dims, strides, box, estr, f32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+            };
+            const void* pout = prim_f32 ? (const void*)c->out_f32 : (const void*)c->out_bf16;
+            if (gp.prim_store && (rc = enc(&gp.pmap, pout, prim_f32))) return rc;
+            if (c->res && (rc = enc(&gp.resmap, c->res, prim_f32))) return rc;
+            if (gp.sec_store && (rc = enc(&gp.hmap, c->out_bf16, false))) return rc;
+            if (!gp.prim_store) gp.pmap = c->res ? gp.resmap : gp.hmap;
+            if (!c->res) gp.resmap = gp.pmap;
+            if (!gp.sec_store) gp.hmap = gp.pmap;
+        }
+    }
 
     // ---- tile shape.  Columns: one or two chunks of BNC.  The 2 x 160 tile halves the L2 traffic per FLOP but
     // quantises the grid more coarsely; estimate both (cycles per k-block: max(MMA, L2 fill at ~43 B/clk/SM)).
