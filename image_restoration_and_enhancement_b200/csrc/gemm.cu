@@ -56,6 +56,7 @@ struct GemmParams {
     int prim_f32;                     // dtype of the primary staging buffer (residual in / same-dtype output in place)
     int prim_store;                   // an output of the primary dtype exists
     int sec_store;                    // bf16 output next to an fp32 primary buffer
+    int epi_mode;                     // EPI_* bit set when it matches a specialised epilogue, else EPI_GENERIC
     int dbg;                          // RG_GEMM_DEBUG bits (perf experiments only): 1 skip units, 2 skip stores, 4 skip residual
     int out_cols;                     // Cout, or Cout / 2 for GEGLU
     CUtensorMap resmap, pmap, hmap;   // residual load, primary store, secondary (bf16) store
@@ -108,21 +109,31 @@ struct RowGeom {
 // finished box to a TMA store.  No global load or store is issued by the math threads, nothing waits for a memory
 // round trip, every byte moves in full 32/64-byte row segments, and ragged tile edges are clipped by the tensor map.
 // Requires Cout % N_TILE == 0 (every unit of every chunk is real), which holds for all UNet / VAE body layers.
-template <int BNC, int NC>
-__device__ __forceinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging, uint64_t* acc_full, uint64_t* acc_empty,
+// MODE: bit set of EPI_* known at compile time (straight-line unit code, four independent column groups in flight),
+// or EPI_GENERIC to read every flag from the parameters at run time.
+enum : int { EPI_GEGLU = 1, EPI_PRIM_F32 = 2, EPI_RES = 4, EPI_PRIM_STORE = 8, EPI_SEC_STORE = 16, EPI_BIAS = 32,
+             EPI_BIASN = 64, EPI_SILU = 128, EPI_SCALE = 256, EPI_GENERIC = 1 << 20 };
+
+template <int BNC, int NC, int MODE>
+__device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging, uint64_t* acc_full, uint64_t* acc_empty,
                                              uint64_t* res_bar_all, uint32_t tmem_base, uint32_t rank, int cluster_id,
                                              int n_clusters, int warp, int lane) {
     using Cfg = GemmCfg<BNC, NC>;
     constexpr int NBUF = Cfg::NBUF, HBUF = Cfg::HBUF;
     const int ew = warp - 2;
     const int q = warp & 3, half = ew >> 2;
-    // everything the unit loop needs, in registers
-    const bool geglu = p.act == 2, silu = p.act == 1;
-    const bool prim_f32 = p.prim_f32 != 0, prim_store = p.prim_store != 0, sec_store = p.sec_store != 0;
-    const bool has_res = p.res != nullptr && !(p.dbg & 4);
-    const bool skip_units = (p.dbg & 1) != 0, skip_store = (p.dbg & 2) != 0;
-    const float scale = p.scale;
-    const float* const bias = p.bias;
+    // everything the unit loop needs, in registers (compile-time constants unless MODE == EPI_GENERIC)
+    constexpr bool G = MODE == EPI_GENERIC;
+    const bool geglu = G ? p.act == 2 : (MODE & EPI_GEGLU) != 0;
+    const bool silu = G ? p.act == 1 : (MODE & EPI_SILU) != 0;
+    const bool prim_f32 = G ? p.prim_f32 != 0 : (MODE & EPI_PRIM_F32) != 0;
+    const bool prim_store = G ? p.prim_store != 0 : (MODE & EPI_PRIM_STORE) != 0;
+    const bool sec_store = G ? p.sec_store != 0 : (MODE & EPI_SEC_STORE) != 0;
+    const bool has_res = G ? (p.res != nullptr && !(p.dbg & 4)) : (MODE & EPI_RES) != 0;
+    const bool skip_units = G && (p.dbg & 1) != 0, skip_store = G && (p.dbg & 2) != 0;
+    const float scale = (G || (MODE & EPI_SCALE)) ? p.scale : 1.0f;
+    const float* const bias = (G || (MODE & EPI_BIAS)) ? p.bias : nullptr;
+    const bool use_bn = G ? p.bias_n != nullptr : (MODE & EPI_BIASN) != 0;
     const int gsh = geglu ? 1 : 0;                        // output column = GEMM column >> gsh
     const int UW = geglu ? 32 : 16;                       // accumulator columns per unit
     const int UPC = BNC / UW;                             // units per chunk
@@ -167,7 +178,7 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams& p, uint8_t* stagi
         if (has_next) box_origin(tile + n_clusters, cw2, ch2, cn2, n_tile2, tni2);
         int n_row = tni * TN + ((row0 + lane) >> lwh);
         if (n_row >= p.N) n_row = p.N - 1;                // padding rows: any valid image (their result is clipped)
-        const float* const bn_row = p.bias_n ? p.bias_n + (long long)n_row * p.bias_n_ld : nullptr;
+        const float* const bn_row = use_bn ? p.bias_n + (long long)n_row * p.bias_n_ld : nullptr;
 #pragma unroll 1
         for (int c = 0; c < NC; ++c) {
             const uint32_t slot = (cc + c) % Cfg::SLOTS, use = (cc + c) / Cfg::SLOTS;
@@ -385,7 +396,21 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     } else {
         // ===================================================================== epilogue (both CTAs, own 128 rows)
         if (p.epi_tma) {
-            epilogue_tma<BNC, NC>(p, staging, acc_full, acc_empty, res_bar, tmem_base, rank, cluster_id, n_clusters, warp, lane);
+#define RG_EPI_CASE(M) case (M): epilogue_tma<BNC, NC, (M)>(p, staging, acc_full, acc_empty, res_bar, tmem_base, rank, cluster_id, n_clusters, warp, lane); break;
+            switch (p.epi_mode) {
+                RG_EPI_CASE(EPI_PRIM_STORE)                                                   // bf16 out (q|k|v, q)
+                RG_EPI_CASE(EPI_PRIM_STORE | EPI_BIAS)                                        // bf16 out + bias
+                RG_EPI_CASE(EPI_PRIM_STORE | EPI_BIAS | EPI_BIASN)                            // resnet conv1 (+ time embedding)
+                RG_EPI_CASE(EPI_PRIM_STORE | EPI_BIAS | EPI_RES)                              // VAE conv2: bf16 residual
+                RG_EPI_CASE(EPI_PRIM_F32 | EPI_PRIM_STORE | EPI_BIAS)                         // fp32 out (proj_in, up/down-sample)
+                RG_EPI_CASE(EPI_PRIM_F32 | EPI_PRIM_STORE | EPI_SEC_STORE | EPI_BIAS)         // fp32 + bf16 out
+                RG_EPI_CASE(EPI_PRIM_F32 | EPI_PRIM_STORE | EPI_BIAS | EPI_RES)               // fp32 stream += (attention out)
+                RG_EPI_CASE(EPI_PRIM_F32 | EPI_PRIM_STORE | EPI_SEC_STORE | EPI_BIAS | EPI_RES)  // conv2 / proj_out with a bf16 copy
+                RG_EPI_CASE(EPI_PRIM_F32 | EPI_SEC_STORE | EPI_BIAS | EPI_RES)                // feed-forward out: fp32 residual, bf16 out
+                RG_EPI_CASE(EPI_GEGLU | EPI_PRIM_STORE | EPI_BIAS)                            // GEGLU
+                default: epilogue_tma<BNC, NC, EPI_GENERIC>(p, staging, acc_full, acc_empty, res_bar, tmem_base, rank, cluster_id, n_clusters, warp, lane); break;
+            }
+#undef RG_EPI_CASE
         } else {
             const int q = warp & 3;                    // TMEM lane quarter this warp may access
             const int half = (warp - 2) >> 2;          // units are dealt alternately to the two warps of a quarter
@@ -745,6 +770,17 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
             if (!gp.prim_store) gp.pmap = c->res ? gp.resmap : gp.hmap;
             if (!c->res) gp.resmap = gp.pmap;
             if (!gp.sec_store) gp.hmap = gp.pmap;
+            int mode = 0;
+            if (c->act == RG_ACT_GEGLU) mode |= 1;       // EPI_GEGLU
+            if (gp.prim_f32) mode |= 2;
+            if (c->res) mode |= 4;
+            if (gp.prim_store) mode |= 8;
+            if (gp.sec_store) mode |= 16;
+            if (c->bias) mode |= 32;
+            if (c->bias_n) mode |= 64;
+            if (c->act == RG_ACT_SILU) mode |= 128;
+            if (c->scale != 1.0f) mode |= 256;
+            gp.epi_mode = gp.dbg ? (1 << 20) : mode;    // debug experiments run the generic (run-time flag) epilogue
         }
     }
 

@@ -21,6 +21,11 @@ elif which == "linear":      # attention out-projection with fp32 residual in/ou
     r = torch.randn((65536, 320), device="cuda")
     for _ in range(4):
         ops.linear(x, w, res=r, out_f32=r.view(1, 1, 65536, 320))
+elif which == "qkv":         # q|k|v projection at 64x64 latents: M=65536, N=960, K=320, bf16 out (epilogue / HBM bound)
+    x = torch.randn((65536, 320), device="cuda").to(torch.bfloat16)
+    w = (torch.randn((960, 320), device="cuda") / 18.0).to(torch.bfloat16)
+    for _ in range(4):
+        ops.linear(x, w, out_bf16=True)
 elif which == "attn":        # self-attention at 64x64 latents: B=16, 8 heads, d=40, N=4096
     qkv = torch.randn((16, 4096, 3, 8, 40), device="cuda").to(torch.bfloat16)
     for _ in range(3):
