@@ -24,12 +24,13 @@ struct GnParams {
     int n_blocks;              // statistics blocks per image (<= RG_GN_MAX_BLOCKS)
 };
 
-__device__ __forceinline__ void load8(const GnParams& p, int n, long long pix, int c0, float (&v)[8]) {
-    // c0 is a multiple of 8 and C1 is a multiple of 8, so a vector never straddles the two sources
-    const void* src; int cs, Cs;
-    if (c0 < p.C1) { src = p.x1; cs = c0; Cs = p.C1; } else { src = p.x2; cs = c0 - p.C1; Cs = p.C2; }
+// Compile-time input dtype: the loads of an unrolled pixel loop stay independent (no branch between them).
+// src / Cs / cs: the thread's source tensor, its channel count and the thread's first channel inside it
+// (c0 is a multiple of 8 and C1 is a multiple of 8, so a vector never straddles the two sources).
+template <bool IN_F32>
+__device__ __forceinline__ void load8(const void* src, int Cs, int cs, const GnParams& p, int n, long long pix, float (&v)[8]) {
     const long long idx = ((long long)n * p.HW + pix) * Cs + cs;
-    if (p.in_f32) {
+    if (IN_F32) {
         const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + idx);
         const float4 a = s[0], b = s[1];
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -52,6 +53,7 @@ __device__ __forceinline__ float* gn_partials(const GnParams& p) { return gn_fin
 // block order in fp64.  No atomics anywhere, so a run is bitwise reproducible and an image's result does not depend
 // on how many other images share the launch.
 // grid = (blocks_per_image, N); block = tpr * rpb threads
+template <bool IN_F32>
 __global__ void __launch_bounds__(512) gn_stats_kernel(const GnParams p) {
     extern __shared__ float s_red[];          // [rpb][tpr][16] thread partials, then [C][2] channel sums
     const int n = blockIdx.y;
@@ -63,9 +65,27 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const GnParams p) {
     const long long p0 = (long long)blockIdx.x * p.pix_per_block;
     long long p1 = p0 + p.pix_per_block;
     if (p1 > p.HW) p1 = p.HW;
-    for (long long pix = p0 + tr; pix < p1; pix += p.rpb) {
+    const bool first = c0 < p.C1;
+    const void* const src = first ? p.x1 : p.x2;
+    const int Cs = first ? p.C1 : p.C2, cs = first ? c0 : c0 - p.C1;
+    long long pix = p0 + tr;
+    for (; pix + 3LL * p.rpb < p1; pix += 4LL * p.rpb) {      // four independent loads in flight per thread
+        float v0[8], v1[8], v2[8], v3[8];
+        load8<IN_F32>(src, Cs, cs, p, n, pix, v0);
+        load8<IN_F32>(src, Cs, cs, p, n, pix + p.rpb, v1);
+        load8<IN_F32>(src, Cs, cs, p, n, pix + 2LL * p.rpb, v2);
+        load8<IN_F32>(src, Cs, cs, p, n, pix + 3LL * p.rpb, v3);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                          // same accumulation order as the scalar loop
+            s[i] += v0[i]; ss[i] += v0[i] * v0[i];
+            s[i] += v1[i]; ss[i] += v1[i] * v1[i];
+            s[i] += v2[i]; ss[i] += v2[i] * v2[i];
+            s[i] += v3[i]; ss[i] += v3[i] * v3[i];
+        }
+    }
+    for (; pix < p1; pix += p.rpb) {
         float v[8];
-        load8(p, n, pix, c0, v);
+        load8<IN_F32>(src, Cs, cs, p, n, pix, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s[i] += v[i]; ss[i] += v[i] * v[i]; }
     }
@@ -121,6 +141,7 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const GnParams p) {
     }
 }
 
+template <bool IN_F32>
 __global__ void __launch_bounds__(512) gn_apply_kernel(const GnParams p) {
     const int n = blockIdx.y;
     const int tc = threadIdx.x % p.tpr, tr = threadIdx.x / p.tpr;
@@ -138,9 +159,7 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const GnParams p) {
     const long long p0 = (long long)blockIdx.x * p.pix_per_block;
     long long p1 = p0 + p.pix_per_block;
     if (p1 > p.HW) p1 = p.HW;
-    for (long long pix = p0 + tr; pix < p1; pix += p.rpb) {
-        float v[8];
-        load8(p, n, pix, c0, v);
+    auto emit = [&](long long pix, float (&v)[8]) {
         const long long o = ((long long)n * p.HW + pix) * p.C + c0;
         if (p.raw) {
             *reinterpret_cast<uint4*>(p.raw + o) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
@@ -153,6 +172,23 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const GnParams p) {
         }
         *reinterpret_cast<uint4*>(p.y + o) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                                                          pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    };
+    const bool first = c0 < p.C1;
+    const void* const src = first ? p.x1 : p.x2;
+    const int Cs = first ? p.C1 : p.C2, cs = first ? c0 : c0 - p.C1;
+    long long pix = p0 + tr;
+    for (; pix + 3LL * p.rpb < p1; pix += 4LL * p.rpb) {      // four independent loads in flight per thread
+        float v0[8], v1[8], v2[8], v3[8];
+        load8<IN_F32>(src, Cs, cs, p, n, pix, v0);
+        load8<IN_F32>(src, Cs, cs, p, n, pix + p.rpb, v1);
+        load8<IN_F32>(src, Cs, cs, p, n, pix + 2LL * p.rpb, v2);
+        load8<IN_F32>(src, Cs, cs, p, n, pix + 3LL * p.rpb, v3);
+        emit(pix, v0); emit(pix + p.rpb, v1); emit(pix + 2LL * p.rpb, v2); emit(pix + 3LL * p.rpb, v3);
+    }
+    for (; pix < p1; pix += p.rpb) {
+        float v[8];
+        load8<IN_F32>(src, Cs, cs, p, n, pix, v);
+        emit(pix, v);
     }
 }
 
@@ -184,11 +220,94 @@ static int fill_gn(const rg_gn_t* g, GnParams& p, dim3& grid, int& threads) {
 }
 
 // ---------------------------------------------------------------------------------------------- LayerNorm
-// one warp per row; the row lives in registers between the two reduction passes
-template <bool IN_F32>
-__global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ x_, long long rows, int C,
+// One warp per row, the row lives in registers between the two reduction passes, and the NEXT row of the warp is
+// already in flight while the current one is reduced (the kernel is a pure HBM stream: fp32 in, bf16 out).
+// EPL = elements per lane = C / 32 (10 / 20 / 40 for SD-1.5), loaded as EPL/VEC vectors of VEC floats.
+template <bool IN_F32, int EPL>
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ x_, long long rows,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, __nv_bfloat16* __restrict__ y) {
+    constexpr int C = EPL * 32;
+    constexpr int VEC = (EPL % 4 == 0) ? 4 : 2;          // floats per vector access
+    constexpr int NV = EPL / VEC;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    constexpr bool AFFINE_IN_REGS = EPL <= 20;           // wider rows re-read gamma / beta from L1 per row
+    float g[AFFINE_IN_REGS ? EPL : 1], bt[AFFINE_IN_REGS ? EPL : 1];
+    if (AFFINE_IN_REGS) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                g[j * VEC + e] = __ldg(gamma + (j * 32 + lane) * VEC + e);
+                bt[j * VEC + e] = __ldg(beta + (j * 32 + lane) * VEC + e);
+            }
+    }
+    auto load_row = [&](long long row, float (&v)[EPL]) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const long long idx = row * C + (j * 32 + lane) * VEC;
+            if (IN_F32) {
+                const float* src = reinterpret_cast<const float*>(x_) + idx;
+                if (VEC == 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(src);
+                    v[j * VEC] = t.x; v[j * VEC + 1] = t.y; v[j * VEC + 2] = t.z; v[j * VEC + 3] = t.w;
+                } else {
+                    const float2 t = *reinterpret_cast<const float2*>(src);
+                    v[j * VEC] = t.x; v[j * VEC + 1] = t.y;
+                }
+            } else {
+                const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(x_) + idx;
+                if (VEC == 4) {
+                    const uint2 u = *reinterpret_cast<const uint2*>(src);
+                    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+                    v[j * VEC] = a.x; v[j * VEC + 1] = a.y; v[j * VEC + 2] = b.x; v[j * VEC + 3] = b.y;
+                } else {
+                    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src));
+                    v[j * VEC] = a.x; v[j * VEC + 1] = a.y;
+                }
+            }
+        }
+    };
+    float cur[EPL], nxt[EPL];
+    if (warp0 < rows) load_row(warp0, cur);
+    for (long long row = warp0; row < rows; row += nwarps) {
+        const bool more = row + nwarps < rows;
+        if (more) load_row(row + nwarps, nxt);
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) sum += cur[i];
+        const float mean = warp_sum(sum) * (1.0f / (float)C);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) { const float d = cur[i] - mean; sq += d * d; }
+        const float rstd = rsqrtf(warp_sum(sq) * (1.0f / (float)C) + eps);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            float o[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const float ga = AFFINE_IN_REGS ? g[j * VEC + e] : __ldg(gamma + (j * 32 + lane) * VEC + e);
+                const float be = AFFINE_IN_REGS ? bt[j * VEC + e] : __ldg(beta + (j * 32 + lane) * VEC + e);
+                o[e] = (cur[j * VEC + e] - mean) * rstd * ga + be;
+            }
+            __nv_bfloat16* dst = y + row * C + (j * 32 + lane) * VEC;
+            if (VEC == 4) *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+            else *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(o[0], o[1]);
+        }
+        if (more) {
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) cur[i] = nxt[i];
+        }
+    }
+}
+
+// generic fallback (any C that is a multiple of 4, up to 1536): one row per warp, no prefetch
+template <bool IN_F32>
+__global__ void __launch_bounds__(256) layernorm_generic_kernel(const void* __restrict__ x_, long long rows, int C,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float eps, __nv_bfloat16* __restrict__ y) {
     constexpr int MAXV = 12;                     // 12 * 32 lanes * 4 = 1536 channels max
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -273,12 +392,12 @@ extern "C" int rg_groupnorm_stats(const rg_gn_t* g, rg_stream_t stream) {
     const size_t smem = ((size_t)threads * 16 + (size_t)p.C * 2) * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(gn_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(gn_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         attr_done = true;
     }
-    cudaError_t me = cudaMemsetAsync(p.sums, 0, (size_t)p.N * sizeof(int), reinterpret_cast<cudaStream_t>(stream));
-    if (me != cudaSuccess) return set_cuda_error(me, "cudaMemsetAsync(groupnorm counters)");
-    gn_stats_kernel<<<grid, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    if (p.in_f32) gn_stats_kernel<true><<<grid, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    else gn_stats_kernel<false><<<grid, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     count_launch();
     return check_launch("gn_stats_kernel");
 }
@@ -289,22 +408,36 @@ extern "C" int rg_groupnorm_apply(const rg_gn_t* g, rg_stream_t stream) {
     int rc = fill_gn(g, p, grid, threads);
     if (rc) return rc;
     if (!g->y) return set_error(RG_ERR_ARG, "groupnorm_apply: null output");
-    gn_apply_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    if (p.in_f32) gn_apply_kernel<true><<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    else gn_apply_kernel<false><<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     count_launch();
     return check_launch("gn_apply_kernel");
+}
+
+template <bool IN_F32, int EPL>
+static void launch_ln(const void* x, int64_t rows, const float* gamma, const float* beta, float eps, void* y, cudaStream_t s) {
+    const int wpb = 8;
+    long long blocks = (rows + wpb - 1) / wpb;
+    const long long cap = (long long)sm_count() * 8;       // persistent: each warp walks rows with a one-row prefetch
+    if (blocks > cap) blocks = cap;
+    layernorm_kernel<IN_F32, EPL><<<(unsigned)blocks, wpb * 32, 0, s>>>(x, rows, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y));
 }
 
 extern "C" int rg_layernorm(const void* x, int32_t in_dtype, int64_t rows, int32_t C, const float* gamma,
                             const float* beta, float eps, void* y, rg_stream_t stream) {
     if (!x || !y || !gamma || !beta) return set_error(RG_ERR_ARG, "layernorm: null pointer");
     if (C % 4 || C > 1536) return set_error(RG_ERR_ARG, "layernorm: C must be a multiple of 4 and <= 1536");
-    const int wpb = 8;
-    const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (in_dtype == RG_DT_F32)
-        layernorm_kernel<true><<<grid, wpb * 32, 0, s>>>(x, rows, C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y));
-    else
-        layernorm_kernel<false><<<grid, wpb * 32, 0, s>>>(x, rows, C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y));
+    const bool f32 = in_dtype == RG_DT_F32;
+    if (C == 320) { if (f32) launch_ln<true, 10>(x, rows, gamma, beta, eps, y, s); else launch_ln<false, 10>(x, rows, gamma, beta, eps, y, s); }
+    else if (C == 640) { if (f32) launch_ln<true, 20>(x, rows, gamma, beta, eps, y, s); else launch_ln<false, 20>(x, rows, gamma, beta, eps, y, s); }
+    else if (C == 1280) { if (f32) launch_ln<true, 40>(x, rows, gamma, beta, eps, y, s); else launch_ln<false, 40>(x, rows, gamma, beta, eps, y, s); }
+    else {
+        const int wpb = 8;
+        const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+        if (f32) layernorm_generic_kernel<true><<<grid, wpb * 32, 0, s>>>(x, rows, C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y));
+        else layernorm_generic_kernel<false><<<grid, wpb * 32, 0, s>>>(x, rows, C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y));
+    }
     count_launch();
     return check_launch("layernorm_kernel");
 }

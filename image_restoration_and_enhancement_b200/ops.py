@@ -40,6 +40,17 @@ def _prof_end(e0, work, kind, desc=""):
         PROFILE.append((e0, e1, work, kind, desc))
 
 
+_GN_WS: dict = {}
+
+
+def _gn_workspace(device, n_floats: int) -> torch.Tensor:
+    key = (device.type, device.index)
+    ws = _GN_WS.get(key)
+    if ws is None or ws.numel() < n_floats:
+        ws = _GN_WS[key] = torch.zeros((max(n_floats, 1 << 20),), dtype=f32, device=device)
+    return ws
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -180,9 +191,9 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, grou
     y = torch.empty((N, H, W, Ct), dtype=bf16, device=x1.device)
     raw = torch.empty((N, H, W, Ct), dtype=bf16, device=x1.device) if want_raw else None
     if sums is None:
-        # RG_GN_WORKSPACE_FLOATS: counters | (mean, rstd) | per-block partials
-        sums = torch.empty((((N + 3) & ~3) + N * groups * 2 + N * GN_MAX_BLOCKS * groups * 2,), dtype=f32,
-                           device=x1.device)
+        # RG_GN_WORKSPACE_FLOATS: counters | (mean, rstd) | per-block partials.  The arrival counters must be zero on
+        # entry and reset themselves, so one zero-initialised workspace per device serves every call of a stream.
+        sums = _gn_workspace(x1.device, ((N + 3) & ~3) + N * groups * 2 + N * GN_MAX_BLOCKS * groups * 2)
     p = RgGn()
     p.x1, p.C1, p.x2, p.C2 = x1.data_ptr(), C1, _ptr(x2), C2
     p.in_dtype, p.N, p.HW, p.groups, p.eps = _dt(x1), N, H * W, groups, eps
