@@ -210,7 +210,7 @@ def run_b200(args) -> int:
     if rank == 0:
         roof = conv_roofline(pipe, dev)
         if world == 1 and not args.no_cpu:
-            pair_s, cores = cpu_unet_pair_seconds(reps=2)
+            pair_s, cores = cpu_unet_pair_seconds(reps=1)
             cpu = {"value": cpu_images_per_sec(pair_s), "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": CPU_SAMPLE, "unet_cfg_pair_seconds": pair_s}
     if world > 1:

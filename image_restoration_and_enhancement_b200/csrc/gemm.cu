@@ -795,7 +795,9 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
     auto waves = [&](int n_tile) { return (int)(((long long)gp.n_pairs_m * ((Cout + n_tile - 1) / n_tile) + clusters - 1) / clusters); };
     if (Cout % 160 == 0) {
         // short K: the epilogue dominates and wants the full double buffering of the 1 x 160 tile (3 TMEM slots)
-        if (Cout % 320 == 0 && gp.total_kblk > 24 && (long long)waves(320) * 865 <= (long long)waves(160) * 625)
+        static int min_kblk = -1;
+        if (min_kblk < 0) { const char* e = getenv("RG_GEMM_NC2_MIN_KBLK"); min_kblk = e ? atoi(e) : 24; }
+        if (Cout % 320 == 0 && gp.total_kblk > min_kblk && (long long)waves(320) * 865 <= (long long)waves(160) * 625)
             return launch_gemm<160, 2>(gp, c->w, ktot, w_ld, stream);
         return launch_gemm<160, 1>(gp, c->w, ktot, w_ld, stream);
     }

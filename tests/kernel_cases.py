@@ -84,7 +84,7 @@ def case_geglu(M=300, K=320, C4=1280, seed=5):
 
 
 def case_conv(N=2, H=16, W=16, Cin=64, Cout=160, k=3, stride=1, pad=1, asym=False, bias=True, bias_n=False,
-              res=None, x2c=0, f32_out=False, seed=10):
+              res=None, x2c=0, f32_out=False, both_out=False, seed=10):
     """3x3 / 1x1 convolution vs F.conv2d.  ``asym``: VAE-encoder downsample (pad (0,1,0,1), stride 2, pad 0)."""
     _setup()
     x = _rand((N, H, W, Cin), seed)
@@ -116,10 +116,36 @@ def case_conv(N=2, H=16, W=16, Cin=64, Cout=160, k=3, stride=1, pad=1, asym=Fals
         r = _rand((N, OH, OW, Cout), seed + 3, 1.0, torch.float32 if res == "f32" else torch.bfloat16)
         ref = ref + r.float().permute(0, 3, 1, 2)
     ob, of = ops.conv2d(x, wp, kh=k, kw=k, stride=2 if asym else stride, pad_t=pad_t, pad_l=pad_l, OH=OH, OW=OW,
-                        x2=x2, bias=b, bias_n=bn, res=r, out_bf16=not f32_out, out_f32=f32_out)
+                        x2=x2, bias=b, bias_n=bn, res=r, out_bf16=both_out or not f32_out, out_f32=both_out or f32_out)
     torch.cuda.synchronize()
+    if both_out:        # fp32 stream + bf16 copy from one epilogue (resnet conv2 / proj_out feeding a down/up-sampler)
+        e32 = rel_l2(of.float().permute(0, 3, 1, 2), ref)
+        e16 = rel_l2(ob.float().permute(0, 3, 1, 2), ref)
+        return max(e32 / TOL_F32, e16 / TOL_BF16), 1.0
     out = (of if f32_out else ob).float().permute(0, 3, 1, 2)
     return rel_l2(out, ref), (TOL_F32 if f32_out else TOL_BF16)
+
+
+def case_conv_strided_out(seed=29):
+    """Parity-split write: a 2x2 conv whose fp32 output lands on every second pixel of a larger tensor (the
+    nearest-2x upsample + 3x3 conv split of unet.py / vae.py)."""
+    _setup()
+    N, H, W, C = 2, 16, 16, 320
+    x = _rand((N, H, W, C), seed)
+    w = _rand((C, C, 2, 2), seed + 1, 1.0 / math.sqrt(C * 4))
+    b = _rand((C,), seed + 2, 0.5, torch.float32)
+    out = torch.zeros((N, 2 * H, 2 * W, C), dtype=torch.float32, device=DEV)
+    sn, sh, sw = out.stride(0), out.stride(1), out.stride(2)
+    errs = []
+    for py in (0, 1):
+        for px in (0, 1):
+            ops.conv2d(x, pack_w(w), kh=2, kw=2, pad_t=1 - py, pad_l=1 - px, OH=H, OW=W, bias=b,
+                       out_f32=out[:, py:, px:], out_strides=(sn, 2 * sh, 2 * sw))
+            xn = F.pad(x.float().permute(0, 3, 1, 2), (1 - px, px, 1 - py, py))
+            ref = F.conv2d(xn, w.float(), b)
+            torch.cuda.synchronize()
+            errs.append(rel_l2(out[:, py::2, px::2].permute(0, 3, 1, 2), ref))
+    return max(errs), TOL_F32
 
 
 # ------------------------------------------------------------------------------------------------ attention
@@ -298,6 +324,13 @@ CASES = {
     "conv1x1": lambda: case_conv(N=2, H=32, W=32, Cin=640, Cout=640, k=1, pad=0, res="f32", f32_out=True, seed=18),
     "conv3x3_vae512_cout3": lambda: case_conv(N=1, H=128, W=128, Cin=128, Cout=3, f32_out=True, seed=19),
     "conv3x3_wide": lambda: case_conv(N=1, H=8, W=256, Cin=64, Cout=64, seed=20),
+    "conv3x3_both_out_res": lambda: case_conv(N=2, H=32, W=32, Cin=640, Cout=640, res="f32", both_out=True, seed=21),
+    "conv3x3_both_out_shortcut": lambda: case_conv(N=2, H=16, W=16, Cin=320, Cout=640, x2c=320, both_out=True, seed=22),
+    "conv3x3_vae_res_bf16": lambda: case_conv(N=1, H=64, W=64, Cin=256, Cout=256, res="bf16", seed=23),
+    "conv3x3_vae_cout512": lambda: case_conv(N=1, H=32, W=32, Cin=512, Cout=512, seed=24),
+    "conv3x3_long_k_2chunk": lambda: case_conv(N=4, H=32, W=32, Cin=1280, Cout=640, bias_n=True, seed=25),
+    "conv2x2_parity_strided_out": case_conv_strided_out,
+    "linear_ff_out_res_f32_bf16out": lambda: case_linear(M=4096, K=1280, N=320, res="f32", seed=26),
     # --- attention
     "attn_self_d40": lambda: case_attention(B=2, heads=8, d=40, Nq=1024),
     "attn_self_d40_4096": lambda: case_attention(B=1, heads=8, d=40, Nq=4096, seed=21),
@@ -308,6 +341,8 @@ CASES = {
     "attn_cross_d160": lambda: case_attention(B=2, heads=8, d=160, Nq=64, Nk=77, seed=26, fused_qkv=False),
     "attn_ragged": lambda: case_attention(B=1, heads=8, d=40, Nq=2542, seed=27),
     "attn_d64": lambda: case_attention(B=1, heads=4, d=64, Nq=300, seed=28),
+    "attn_d128": lambda: case_attention(B=1, heads=2, d=128, Nq=700, seed=29),
+    "attn_many_items": lambda: case_attention(B=4, heads=8, d=40, Nq=2048, seed=30),       # > 148 items: persistent loop
     # --- norms
     "gn_f32_silu": lambda: case_groupnorm(),
     "gn_concat_raw": lambda: case_groupnorm(N=2, H=8, W=8, C1=1280, C2=640, raw=True, seed=31),

@@ -279,4 +279,6 @@ def test_weight_packing_identities():
     assert float((out - ref).abs().max()) < 1e-5
     wg, bg = torch.arange(640.0)[:, None].repeat(1, 2), torch.arange(640.0)
     wi, bi = interleave_geglu(wg, bg)
-    assert bi[:80].tolist() == list(range(80)) and bi[80:160].tolist() == list(range(320, 400)) and torch.equal(wi[:, 0], bi)
+    # units of 32 rows: 16 value rows followed by their 16 gate rows (GEMM epilogue, csrc/gemm.cu)
+    assert bi[:16].tolist() == list(range(16)) and bi[16:32].tolist() == list(range(320, 336))
+    assert bi[32:48].tolist() == list(range(16, 32)) and torch.equal(wi[:, 0], bi)

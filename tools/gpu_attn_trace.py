@@ -10,7 +10,7 @@ d = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 lib = _lib.load()
 qkv = torch.randn((16, N, 3, 8, d), device="cuda").to(torch.bfloat16)
-buf = torch.zeros((8, 64, 8), dtype=torch.int64, device="cuda")
+buf = torch.zeros((18, 64, 8), dtype=torch.int64, device="cuda")
 ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], d ** -0.5)
 lib.rg_debug_attn_trace.argtypes = [__import__("ctypes").c_void_p]
 lib.rg_debug_attn_trace(buf.data_ptr())
@@ -19,7 +19,7 @@ torch.cuda.synchronize()
 lib.rg_debug_attn_trace(None)
 t = buf.cpu()
 names = ["wait s_full", "ldtm", "s_free+max", "rescale chk", "exp+pack", "wait pv_done", "sttm+wait", "arrive"]
-for w in (0, 4):
+for w in (0, 4, 8, 12):
     tt = t[w]
     n = int((tt[:, 0] > 0).sum())
     if n < 3:
