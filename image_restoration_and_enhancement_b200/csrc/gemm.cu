@@ -56,6 +56,7 @@ struct GemmParams {
     int prim_f32;                     // dtype of the primary staging buffer (residual in / same-dtype output in place)
     int prim_store;                   // an output of the primary dtype exists
     int sec_store;                    // bf16 output next to an fp32 primary buffer
+    int ksplit, kper;                 // split-K: each tile covers k-blocks [ks*kper, (ks+1)*kper) and is reduce-added
     int epi_mode;                     // EPI_* bit set when it matches a specialised epilogue, else EPI_GENERIC
     int dbg;                          // RG_GEMM_DEBUG bits (perf experiments only): 1 skip units, 2 skip stores, 4 skip residual
     int out_cols;                     // Cout, or Cout / 2 for GEGLU
@@ -129,7 +130,8 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
     const bool prim_f32 = G ? p.prim_f32 != 0 : (MODE & EPI_PRIM_F32) != 0;
     const bool prim_store = G ? p.prim_store != 0 : (MODE & EPI_PRIM_STORE) != 0;
     const bool sec_store = G ? p.sec_store != 0 : (MODE & EPI_SEC_STORE) != 0;
-    const bool has_res = G ? (p.res != nullptr && !(p.dbg & 4)) : (MODE & EPI_RES) != 0;
+    // (split-K reads the residual with plain loads in its leading split only: no TMA prefetch chain)
+    const bool has_res = G ? (p.res != nullptr && !(p.dbg & 4) && p.ksplit == 1) : (MODE & EPI_RES) != 0;
     const bool skip_units = G && (p.dbg & 1) != 0, skip_store = G && (p.dbg & 2) != 0;
     const float scale = (G || (MODE & EPI_SCALE)) ? p.scale : 1.0f;
     const float* const bias = (G || (MODE & EPI_BIAS)) ? p.bias : nullptr;
@@ -142,7 +144,8 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
     uint8_t* const hbuf0 = pbuf0 + NBUF * 2048;
     uint64_t* const res_bar = res_bar_all + ew * NBUF;
     const uint32_t acc_empty_leader = mapa_shared(smem_u32(acc_empty), 0);
-    const int total_tiles = p.n_pairs_m * p.n_tiles_n;
+    const int total_tiles = p.n_pairs_m * p.n_tiles_n * p.ksplit;
+    const bool split = G && p.ksplit > 1;                 // split-K tiles are reduce-added into a zeroed fp32 output
     const int TW = 1 << p.lw, TH = 1 << p.lh, lwh = p.lw + p.lh, TN = 128 >> lwh;
     const int row0 = q * 32;
     const int res_bytes = prim_f32 ? 2048 : 1024;
@@ -151,8 +154,9 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
 
     // box origin (w, h, n) of this warp's 32 rows in tile `tile`
     auto box_origin = [&](int tile, int& cw, int& ch, int& cn, int& n_tile, int& tni) {
-        const int mp = tile / p.n_tiles_n;
-        n_tile = tile - mp * p.n_tiles_n;
+        const int t2 = tile / p.ksplit;
+        const int mp = t2 / p.n_tiles_n;
+        n_tile = t2 - mp * p.n_tiles_n;
         const int m_tile = 2 * mp + (int)rank;
         const int twi = m_tile % p.tiles_w;
         const int rest = m_tile / p.tiles_w;
@@ -178,7 +182,18 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
         if (has_next) box_origin(tile + n_clusters, cw2, ch2, cn2, n_tile2, tni2);
         int n_row = tni * TN + ((row0 + lane) >> lwh);
         if (n_row >= p.N) n_row = p.N - 1;                // padding rows: any valid image (their result is clipped)
-        const float* const bn_row = use_bn ? p.bias_n + (long long)n_row * p.bias_n_ld : nullptr;
+        const bool lead = !split || (tile % p.ksplit) == 0;      // the split that adds bias / residual
+        const float* const bn_row = (use_bn && lead) ? p.bias_n + (long long)n_row * p.bias_n_ld : nullptr;
+        const float* const bias_t = lead ? bias : nullptr;
+        const float* res_row = nullptr;                    // split-K only: this lane's residual row (fp32), if it is a real pixel
+        if (split && lead && p.res) {
+            const int row = row0 + lane;
+            const int ow = cw - (row0 & (TW - 1)) + (row & (TW - 1));
+            const int oh = ch - ((row0 >> p.lw) & (TH - 1)) + ((row >> p.lw) & (TH - 1));
+            const int n = tni * TN + (row >> lwh);
+            if (ow < p.OW && oh < p.OH && n < p.N)
+                res_row = reinterpret_cast<const float*>(p.res) + (long long)n * p.osn + (long long)oh * p.osh + (long long)ow * p.osw;
+        }
 #pragma unroll 1
         for (int c = 0; c < NC; ++c) {
             const uint32_t slot = (cc + c) % Cfg::SLOTS, use = (cc + c) / Cfg::SLOTS;
@@ -224,9 +239,9 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
-                        if (bias) {
-                            ba = __ldg(reinterpret_cast<const float4*>(bias + gcol + 4 * j));
-                            bg = __ldg(reinterpret_cast<const float4*>(bias + gcol + 16 + 4 * j));
+                        if (bias_t) {
+                            ba = __ldg(reinterpret_cast<const float4*>(bias_t + gcol + 4 * j));
+                            bg = __ldg(reinterpret_cast<const float4*>(bias_t + gcol + 16 + 4 * j));
                         }
                         const float y0 = fmaf(__uint_as_float(va[4 * j]), scale, ba.x) * gelu_fast_f(fmaf(__uint_as_float(vg[4 * j]), scale, bg.x));
                         const float y1 = fmaf(__uint_as_float(va[4 * j + 1]), scale, ba.y) * gelu_fast_f(fmaf(__uint_as_float(vg[4 * j + 1]), scale, bg.y));
@@ -241,9 +256,13 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
                     for (int j = 0; j < 4; ++j) {
                         float y0 = __uint_as_float(va[4 * j]) * scale, y1 = __uint_as_float(va[4 * j + 1]) * scale;
                         float y2 = __uint_as_float(va[4 * j + 2]) * scale, y3 = __uint_as_float(va[4 * j + 3]) * scale;
-                        if (bias) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + gcol + 4 * j));
+                        if (bias_t) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias_t + gcol + 4 * j));
                             y0 += b.x; y1 += b.y; y2 += b.z; y3 += b.w;
+                        }
+                        if (G && res_row) {
+                            const float4 r = *reinterpret_cast<const float4*>(res_row + gcol + 4 * j);
+                            y0 += r.x; y1 += r.y; y2 += r.z; y3 += r.w;
                         }
                         if (bn_row) {
                             const float4 b = __ldg(reinterpret_cast<const float4*>(bn_row + gcol + 4 * j));
@@ -271,7 +290,8 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0 && !skip_store) {
-                    if (prim_store) tma_store_4d(&p.pmap, pb, ocol, cw, ch, cn);
+                    if (split) tma_reduce_add_4d(&p.pmap, pb, ocol, cw, ch, cn);
+                    else if (prim_store) tma_store_4d(&p.pmap, pb, ocol, cw, ch, cn);
                     if (sec_store) tma_store_4d(&p.hmap, hb, ocol, cw, ch, cn);
                     bulk_commit();
                 }
@@ -324,7 +344,8 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
 
-    const int total_tiles = p.n_pairs_m * p.n_tiles_n;
+    // work items: (pair of 128-pixel tiles, column tile, K split); the K split is the fastest index
+    const int total_tiles = p.n_pairs_m * p.n_tiles_n * p.ksplit;
     const int TW = 1 << p.lw, TH = 1 << p.lh;
 
     if (warp == 0) {
@@ -332,17 +353,20 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-                const int mp = tile / p.n_tiles_n, n_tile = tile - mp * p.n_tiles_n;
+                const int ks = tile % p.ksplit, t2 = tile / p.ksplit;
+                const int mp = t2 / p.n_tiles_n, n_tile = t2 - mp * p.n_tiles_n;
                 const int m_tile = 2 * mp + (int)rank;
                 const int twi = m_tile % p.tiles_w;
                 const int rest = m_tile / p.tiles_w;
                 const int thi = rest % p.tiles_h, tni = rest / p.tiles_h;
                 const int w0 = twi * TW, h0 = thi * TH, n0 = tni * (128 >> (p.lw + p.lh));   // n0 >= N: zero fill
                 const int brow = n_tile * Cfg::N_TILE + (int)rank * (BNC / 2);
+                const int kb0 = ks * p.kper, kb1 = kb0 + p.kper < p.total_kblk ? kb0 + p.kper : p.total_kblk;
                 int kblk = 0;
                 for (int it = 0; it < p.n_items; ++it) {
                     const GemmItem item = p.items[it];
-                    for (int cb = 0; cb < item.nblk; ++cb, ++kblk) {
+                    if (kblk + item.nblk <= kb0) { kblk += item.nblk; continue; }        // before this split's range
+                    for (int cb = kblk < kb0 ? kb0 - kblk : 0; cb < item.nblk && kblk + cb < kb1; ++cb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                         const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
@@ -350,10 +374,12 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
                         tma_load_4d_pair(sa, &p.amap[item.map], fb, cb * 64, w0 + item.dw, h0 + item.dh, n0);
 #pragma unroll
                         for (int c = 0; c < NC; ++c)
-                            tma_load_2d_pair(sa + Cfg::A_BYTES + c * Cfg::B_CHUNK_BYTES, &p.bmap, fb, kblk * 64,
+                            tma_load_2d_pair(sa + Cfg::A_BYTES + c * Cfg::B_CHUNK_BYTES, &p.bmap, fb, (kblk + cb) * 64,
                                              brow + c * BNC);
                         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                     }
+                    kblk += item.nblk;
+                    if (kblk >= kb1) break;
                 }
             }
         }
@@ -372,7 +398,9 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
                     d_tmem[c] = tmem_base + slot * BNC;
                 }
                 tc_fence_after();
-                for (int kb = 0; kb < p.total_kblk; ++kb) {
+                const int ks = tile % p.ksplit;
+                const int kb0 = ks * p.kper, kb1 = kb0 + p.kper < p.total_kblk ? kb0 + p.kper : p.total_kblk;
+                for (int kb = 0; kb < kb1 - kb0; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -626,7 +654,7 @@ static int launch_gemm(GemmParams& gp, const void* w, long long ktot, long long 
     }
     gp.n_tiles_n = (gp.Cout + Cfg::N_TILE - 1) / Cfg::N_TILE;
     if (gp.Cout % Cfg::N_TILE != 0) gp.epi_tma = 0;        // the TMA epilogue assumes every 16-column unit is real
-    const int total = gp.n_pairs_m * gp.n_tiles_n;
+    const int total = gp.n_pairs_m * gp.n_tiles_n * gp.ksplit;
     const int max_clusters = sm_count() / 2;
     const int clusters = total < max_clusters ? total : max_clusters;
     conv_gemm_kernel<BNC, NC><<<2 * clusters, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(gp);
@@ -791,7 +819,22 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
         if (Cout % 32 != 0 || !c->out_bf16 || c->out_f32 || c->res || c->bias_n || !aligned)
             return set_error(RG_ERR_ARG, "rg_conv2d: GEGLU needs Cout % 32 == 0 and a 16-B aligned bf16 output only");
     }
+    gp.ksplit = 1;
+    gp.kper = gp.total_kblk;
     const int clusters = sm_count() / 2;
+    // ---- split-K (x2) for the few-pixel levels with a long K (8x8 and below in the UNet): both halves are reduce-added
+    // by TMA into the zero-initialised fp32 output; x + y is commutative, so the result does not depend on arrival order.
+    if (gp.epi_tma && Cout % 160 == 0 && gp.prim_f32 && gp.prim_store && !gp.sec_store && c->act == RG_ACT_NONE &&
+        gp.total_kblk >= 32 && OH * OW <= 64 &&          /* decided per image, never by N: results stay batch-invariant */
+        (!c->res || c->res_dtype == RG_DT_F32) && c->res != (const void*)c->out_f32 &&
+        c->out_stride_w == Cout && c->out_stride_h == (long long)OW * Cout && c->out_stride_n == (long long)OH * OW * Cout) {
+        cudaError_t e = cudaMemsetAsync(c->out_f32, 0, (size_t)N * OH * OW * Cout * sizeof(float), stream);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(split-K output)");
+        gp.ksplit = 2;
+        gp.kper = (gp.total_kblk + 1) / 2;
+        gp.epi_mode = 1 << 20;                           // run-time-flag epilogue
+        return launch_gemm<160, 1>(gp, c->w, ktot, w_ld, stream);
+    }
     auto waves = [&](int n_tile) { return (int)(((long long)gp.n_pairs_m * ((Cout + n_tile - 1) / n_tile) + clusters - 1) / clusters); };
     if (Cout % 160 == 0) {
         // short K: the epilogue dominates and wants the full double buffering of the 1 x 160 tile (3 TMEM slots)

@@ -152,8 +152,11 @@ class UNetB200:
         N = x.shape[0]
         y1, raw = ops.groupnorm(x, r.g1, r.b1, eps=1e-5, silu=True, x2=skip, want_raw=r.shortcut)
         bn = temb_all[:, r.temb_off:r.temb_off + r.cout]
-        h, _ = ops.conv2d(y1, r.w1, kh=3, kw=3, pad_t=1, pad_l=1, bias=r.cb1, bias_n=bn, out_bf16=True)
-        y2, _ = ops.groupnorm(h, r.g2, r.b2, eps=1e-5, silu=True)
+        # few output pixels (the 8x8 level): an fp32 output lets the GEMM split K across two clusters per tile
+        small = x.shape[1] * x.shape[2] <= 64          # per image, never by batch size: results stay batch-invariant
+        hb, hf = ops.conv2d(y1, r.w1, kh=3, kw=3, pad_t=1, pad_l=1, bias=r.cb1, bias_n=bn, out_bf16=not small,
+                            out_f32=small)
+        y2, _ = ops.groupnorm(hf if small else hb, r.g2, r.b2, eps=1e-5, silu=True)
         if r.shortcut:
             ob, of = ops.conv2d(y2, r.w2, kh=3, kw=3, pad_t=1, pad_l=1, x2=raw, bias=r.cb2, out_f32=True,
                                 out_bf16=want_bf16)

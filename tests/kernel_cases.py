@@ -330,6 +330,8 @@ CASES = {
     "conv3x3_vae_cout512": lambda: case_conv(N=1, H=32, W=32, Cin=512, Cout=512, seed=24),
     "conv3x3_long_k_2chunk": lambda: case_conv(N=4, H=32, W=32, Cin=1280, Cout=640, bias_n=True, seed=25),
     "conv2x2_parity_strided_out": case_conv_strided_out,
+    "conv3x3_unet8_splitk_b16": lambda: case_conv(N=16, H=8, W=8, Cin=1280, Cout=1280, bias_n=True, f32_out=True, seed=27),
+    "conv3x3_unet8_splitk_shortcut": lambda: case_conv(N=16, H=8, W=8, Cin=1280, Cout=1280, x2c=2560, f32_out=True, seed=28),
     "linear_ff_out_res_f32_bf16out": lambda: case_linear(M=4096, K=1280, N=320, res="f32", seed=26),
     # --- attention
     "attn_self_d40": lambda: case_attention(B=2, heads=8, d=40, Nq=1024),
