@@ -44,8 +44,8 @@ __device__ __forceinline__ void load8(const void* src, int Cs, int cs, const GnP
     }
 }
 
-// workspace layout (floats): [N counters (int)] [N][G][2] (mean, rstd) [N][blocks][G][2] partial (sum, sumsq)
-__device__ __forceinline__ float* gn_final(const GnParams& p) { return p.sums + ((p.N + 3) & ~3); }
+// workspace layout (floats): [RG_GN_MAX_IMAGES counters (int), zero between launches] [N][G][2] (mean, rstd) [N][blocks][G][2] partial (sum, sumsq)
+__device__ __forceinline__ float* gn_final(const GnParams& p) { return p.sums + RG_GN_MAX_IMAGES; }
 __device__ __forceinline__ float* gn_partials(const GnParams& p) { return gn_final(p) + (long long)p.N * p.groups * 2; }
 
 // Deterministic, batch-invariant statistics: every block reduces a fixed slice of one image in a fixed order and
@@ -198,6 +198,7 @@ static int fill_gn(const rg_gn_t* g, GnParams& p, dim3& grid, int& threads) {
     if (g->C1 % 8 || g->C2 % 8 || C % g->groups || g->groups > 64 || C / 8 > 512)
         return set_error(RG_ERR_ARG, "groupnorm: channels must be multiples of 8 (<= 4096) and divisible by groups");
     if (g->C2 && !g->x2) return set_error(RG_ERR_ARG, "groupnorm: C2 without x2");
+    if (g->N < 1 || g->N > RG_GN_MAX_IMAGES) return set_error(RG_ERR_ARG, "groupnorm: batch size out of range");
     p.x1 = g->x1; p.x2 = g->x2; p.C1 = g->C1; p.C2 = g->C2; p.C = C;
     p.in_f32 = g->in_dtype == RG_DT_F32;
     p.N = g->N; p.HW = g->HW; p.groups = g->groups; p.cpg = C / g->groups; p.eps = g->eps;

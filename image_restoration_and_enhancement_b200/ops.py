@@ -17,6 +17,7 @@ from ._lib import (RG_ACT_GEGLU, RG_ACT_NONE, RG_ACT_SILU, RG_DT_BF16, RG_DT_F32
                    RgSched, check)
 
 bf16, f32 = torch.bfloat16, torch.float32
+GN_MAX_IMAGES = 1024      # RG_GN_MAX_IMAGES: fixed-size counter area in front of the GroupNorm workspace
 GN_MAX_BLOCKS = 64        # RG_GN_MAX_BLOCKS in include/restoragen.h
 
 # When set to a list, conv2d / attention append (start_event, end_event, algorithmic_flops, kind) per launch
@@ -193,7 +194,8 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, grou
     if sums is None:
         # RG_GN_WORKSPACE_FLOATS: counters | (mean, rstd) | per-block partials.  The arrival counters must be zero on
         # entry and reset themselves, so one zero-initialised workspace per device serves every call of a stream.
-        sums = _gn_workspace(x1.device, ((N + 3) & ~3) + N * groups * 2 + N * GN_MAX_BLOCKS * groups * 2)
+        assert N <= GN_MAX_IMAGES
+        sums = _gn_workspace(x1.device, GN_MAX_IMAGES + N * groups * 2 + N * GN_MAX_BLOCKS * groups * 2)
     p = RgGn()
     p.x1, p.C1, p.x2, p.C2 = x1.data_ptr(), C1, _ptr(x2), C2
     p.in_dtype, p.N, p.HW, p.groups, p.eps = _dt(x1), N, H * W, groups, eps

@@ -125,12 +125,13 @@ int rg_softmax_rows(void* x, int64_t rows, int32_t cols, int64_t ld, rg_stream_t
  *   reduction order is fixed, so results are bitwise reproducible and independent of the batch size;
  *   rg_groupnorm_apply writes y = silu?((x-mean)*rstd*gamma+beta) as bf16 and optionally the raw
  *   concatenated input as bf16 (feeds the fused 1x1 shortcut).
- *   The first ((N+3)&~3) words of the workspace are block-arrival counters: they must be ZERO when
+ *   The first RG_GN_MAX_IMAGES words of the workspace are block-arrival counters: they must be ZERO when
  *   rg_groupnorm_stats is enqueued and are reset by the kernel, so a workspace zeroed once can be reused
  *   by every later call on the same stream.
  * ------------------------------------------------------------------------------------------- */
 #define RG_GN_MAX_BLOCKS 64
-#define RG_GN_WORKSPACE_FLOATS(N, G) ((((N) + 3) & ~3) + (N) * (G) * 2 + (N) * RG_GN_MAX_BLOCKS * (G) * 2)
+#define RG_GN_MAX_IMAGES 1024   /* the counter area has a FIXED size so that one workspace serves any batch size */
+#define RG_GN_WORKSPACE_FLOATS(N, G) (RG_GN_MAX_IMAGES + (N) * (G) * 2 + (N) * RG_GN_MAX_BLOCKS * (G) * 2)
 
 typedef struct rg_gn {
     const void* x1; int32_t C1;     /* first source  [N][HW][C1] */

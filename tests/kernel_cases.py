@@ -192,6 +192,26 @@ def case_groupnorm(N=2, H=16, W=16, C1=320, C2=0, in_f32=True, silu=True, eps=1e
     return err, TOL_BF16
 
 
+def case_groupnorm_shapes_agree(seed=34):
+    """GroupNorm is batch-invariant BITWISE: a batch of 16 against each image normalised on its own (fp32 two-source
+    input with raw copy)."""
+    _setup()
+    N, H, W, C1, C2 = 16, 16, 16, 640, 320
+    x1 = _rand((N, H, W, C1), seed, 1.5, torch.float32) + 0.3
+    x2 = _rand((N, H, W, C2), seed + 1, 0.7, torch.float32) - 0.2
+    gamma = _rand((C1 + C2,), seed + 2, 0.2, torch.float32) + 1.0
+    beta = _rand((C1 + C2,), seed + 3, 0.2, torch.float32)
+    y, r = ops.groupnorm(x1, gamma, beta, silu=True, x2=x2, want_raw=True)
+    ref = F.silu(F.group_norm(torch.cat([x1, x2], dim=3).permute(0, 3, 1, 2), 32, gamma, beta, 1e-5))
+    err = rel_l2(y.float().permute(0, 3, 1, 2), ref)
+    bad = 0
+    for n in (0, 7, 15):
+        y1, r1 = ops.groupnorm(x1[n:n + 1].contiguous(), gamma, beta, silu=True, x2=x2[n:n + 1].contiguous(), want_raw=True)
+        torch.cuda.synchronize()
+        bad += int((y1 != y[n:n + 1]).sum()) + int((r1 != r[n:n + 1]).sum())
+    return (err if bad == 0 else 1.0), TOL_BF16
+
+
 def case_layernorm(rows=1000, C=320, in_f32=True, seed=40):
     _setup()
     x = _rand((rows, C), seed, 2.0, torch.float32 if in_f32 else torch.bfloat16) + 0.5
@@ -350,6 +370,10 @@ CASES = {
     "gn_concat_raw": lambda: case_groupnorm(N=2, H=8, W=8, C1=1280, C2=640, raw=True, seed=31),
     "gn_bf16_nosilu_eps6": lambda: case_groupnorm(N=1, H=64, W=64, C1=128, in_f32=False, silu=False, eps=1e-6, seed=32),
     "gn_big": lambda: case_groupnorm(N=1, H=256, W=256, C1=128, in_f32=False, seed=33),
+    "gn_b16_f32": lambda: case_groupnorm(N=16, H=32, W=32, C1=640, seed=35),
+    "gn_b16_bf16_tiny": lambda: case_groupnorm(N=16, H=8, W=8, C1=1280, in_f32=False, seed=36),
+    "gn_b16_c2560": lambda: case_groupnorm(N=16, H=8, W=8, C1=1280, C2=1280, raw=True, seed=37),
+    "gn_batch_invariant_bitwise": case_groupnorm_shapes_agree,
     "ln_f32_320": lambda: case_layernorm(),
     "ln_bf16_1280": lambda: case_layernorm(rows=333, C=1280, in_f32=False, seed=42),
     "softmax_rows": lambda: case_softmax_rows(),

@@ -49,11 +49,12 @@ def test_batched_call_equals_separate_calls():
     pipe = mc._cache[("pipe", "img2img", 0)]
     g = torch.Generator().manual_seed(5)
     pe, ne = torch.randn((1, 77, 768), generator=g).cuda(), torch.randn((1, 77, 768), generator=g).cuda()
-    imgs = np.stack([mc.synth_image(31 + i, 256, 256) for i in range(2)])
+    nb = 5        # odd on purpose: UNet batch 10 under CFG, VAE batch 5 -- mixed batch sizes share the GroupNorm workspace
+    imgs = np.stack([mc.synth_image(31 + i, 256, 256) for i in range(nb)])
     kw = dict(prompt_embeds=pe, negative_prompt_embeds=ne, strength=0.5, num_inference_steps=10, guidance_scale=5.0,
               output_type="np_u8")
-    both = pipe(image=imgs, generator=[torch.Generator(device="cuda").manual_seed(42) for _ in range(2)], **kw).images
-    for i in range(2):
+    both = pipe(image=imgs, generator=[torch.Generator(device="cuda").manual_seed(42) for _ in range(nb)], **kw).images
+    for i in (0, nb - 1):
         one = pipe(image=imgs[i:i + 1], generator=torch.Generator(device="cuda").manual_seed(42), **kw).images
         # every kernel is batch-invariant (fixed reduction orders, GroupNorm split independent of N): bitwise equal
         assert (both[i:i + 1] == one).all(), f"image {i}: batched vs single PSNR {mc.psnr_u8(both[i:i + 1], one):.2f} dB"
