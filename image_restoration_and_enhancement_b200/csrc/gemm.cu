@@ -63,10 +63,10 @@ struct GemmParams {
     CUtensorMap resmap, pmap, hmap;   // residual load, primary store, secondary (bf16) store
 };
 
-constexpr int kGemmThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
-constexpr int kEpiWarps = 8;
+// warp 0 TMA, warp 1 MMA, warps 2..EW+1 epilogue (EW / 4 per TMEM lane quarter).  EW = 8 for main-loop-bound shapes
+// (deep operand pipeline), EW = 16 for the short-K GEMMs of the transformer blocks whose epilogue is the bottleneck.
 
-template <int BNC, int NC>
+template <int BNC, int NC, int EW>
 struct GemmCfg {
     static constexpr int BM = 128, BK = 64;                   // per CTA; the pair computes 256 rows
     static constexpr int N_TILE = BNC * NC;
@@ -75,10 +75,13 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + NC * B_CHUNK_BYTES;
     // per epilogue warp: NBUF primary buffers [32 rows][16 fp32] (residual in, result in place, TMA store out) and
     // HBUF secondary buffers [32 rows][16 bf16]; the direct (non-TMA) path uses the first two primaries to transpose
-    static constexpr int NBUF = NC == 1 ? 3 : 2;
-    static constexpr int HBUF = NC == 1 ? 2 : 1;
+    static constexpr int NBUF = (NC == 1 && EW == 8) ? 3 : 2;
+    static constexpr int HBUF = (NC == 1 && EW == 8) ? 2 : 1;
     static constexpr int WARP_STAGING = NBUF * 2048 + HBUF * 1024;
-    static constexpr int STAGING_BYTES = kEpiWarps * WARP_STAGING;
+    static constexpr int STAGING_BYTES = EW * WARP_STAGING;
+    static constexpr int THREADS = (EW + 2) * 32;
+    static constexpr int PARTS = EW / 4;                        // epilogue warps per TMEM lane quarter
+    static_assert(EW == 8 || EW == 16, "EW");
     static constexpr int BAR_BYTES = 512;
     static constexpr int MAX_STAGES = (227 * 1024 - 1024 - STAGING_BYTES - BAR_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
@@ -89,7 +92,7 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;
     static_assert(BNC % 32 == 0 && BNC >= 32 && BNC <= 256, "BNC");
     static_assert(SLOTS >= NC + (NC > 1 ? 1 : 1), "TMEM ring too small");
-    static_assert((2 * STAGES + 2 * SLOTS + kEpiWarps * NBUF) * 8 + 8 <= BAR_BYTES, "barrier area");
+    static_assert((2 * STAGES + 2 * SLOTS + EW * NBUF) * 8 + 8 <= BAR_BYTES, "barrier area");
     static_assert(B_CHUNK_BYTES % 1024 == 0, "operand tiles must stay 1024-B aligned");
 };
 
@@ -115,14 +118,15 @@ struct RowGeom {
 enum : int { EPI_GEGLU = 1, EPI_PRIM_F32 = 2, EPI_RES = 4, EPI_PRIM_STORE = 8, EPI_SEC_STORE = 16, EPI_BIAS = 32,
              EPI_BIASN = 64, EPI_SILU = 128, EPI_SCALE = 256, EPI_GENERIC = 1 << 20 };
 
-template <int BNC, int NC, int MODE>
+template <int BNC, int NC, int EW, int MODE>
 __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging, uint64_t* acc_full, uint64_t* acc_empty,
                                              uint64_t* res_bar_all, uint32_t tmem_base, uint32_t rank, int cluster_id,
                                              int n_clusters, int warp, int lane) {
-    using Cfg = GemmCfg<BNC, NC>;
+    using Cfg = GemmCfg<BNC, NC, EW>;
     constexpr int NBUF = Cfg::NBUF, HBUF = Cfg::HBUF;
     const int ew = warp - 2;
-    const int q = warp & 3, half = ew >> 2;
+    constexpr int PARTS = Cfg::PARTS;
+    const int q = warp & 3, part = ew >> 2;               // units part, part + PARTS, .. of every chunk are this warp's
     // everything the unit loop needs, in registers (compile-time constants unless MODE == EPI_GENERIC)
     constexpr bool G = MODE == EPI_GENERIC;
     const bool geglu = G ? p.act == 2 : (MODE & EPI_GEGLU) != 0;
@@ -139,7 +143,7 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
     const int gsh = geglu ? 1 : 0;                        // output column = GEMM column >> gsh
     const int UW = geglu ? 32 : 16;                       // accumulator columns per unit
     const int UPC = BNC / UW;                             // units per chunk
-    const int CNT = (UPC - half + 1) / 2;                 // units per chunk handled by this warp (u = half, half+2, ..)
+    const int CNT = (UPC - part + PARTS - 1) / PARTS;     // units per chunk handled by this warp
     uint8_t* const pbuf0 = staging + ew * Cfg::WARP_STAGING;
     uint8_t* const hbuf0 = pbuf0 + NBUF * 2048;
     uint64_t* const res_bar = res_bar_all + ew * NBUF;
@@ -151,6 +155,7 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
     const int res_bytes = prim_f32 ? 2048 : 1024;
     const int sw = (lane >> 1) & 3;                       // SWIZZLE_64B phase of this lane's 64-byte fp32 row
     const int fo = lane * 64, ho = lane * 32;
+    const int hsw = (lane >> 2) & 1;                      // SWIZZLE_32B phase of this lane's 32-byte bf16 row
 
     // box origin (w, h, n) of this warp's 32 rows in tile `tile`
     auto box_origin = [&](int tile, int& cw, int& ch, int& cn, int& n_tile, int& tni) {
@@ -173,7 +178,7 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
     if (cluster_id < total_tiles) box_origin(cluster_id, cw, ch, cn, n_tile, tni);
     if (has_res && lane == 0 && CNT > 0 && cluster_id < total_tiles && !skip_units) {      // very first residual box
         mbar_expect_tx(&res_bar[0], res_bytes);
-        tma_load_4d(pbuf0, &p.resmap, &res_bar[0], (n_tile * Cfg::N_TILE + half * UW) >> gsh, cw, ch, cn);
+        tma_load_4d(pbuf0, &p.resmap, &res_bar[0], (n_tile * Cfg::N_TILE + part * UW) >> gsh, cw, ch, cn);
     }
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, cc += NC) {
         // next tile's origin: target of the residual prefetch issued from this tile's last unit
@@ -203,7 +208,7 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
             const int gcol0 = n_tile * Cfg::N_TILE + c * BNC;
 #pragma unroll 1
             for (int k = 0; k < CNT && !skip_units; ++k, ++A) {
-                const int u = half + 2 * k;
+                const int u = part + PARTS * k;
                 const int gcol = gcol0 + u * UW;                               // GEMM column (bias index)
                 const int ocol = gcol >> gsh;                                  // output column
                 const int buf = A % NBUF;
@@ -217,13 +222,13 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
                         const int nb = (A + 1) % NBUF;
                         if (k + 1 < CNT) {
                             mbar_expect_tx(&res_bar[nb], res_bytes);
-                            tma_load_4d(pbuf0 + nb * 2048, &p.resmap, &res_bar[nb], (gcol + 2 * UW) >> gsh, cw, ch, cn);
+                            tma_load_4d(pbuf0 + nb * 2048, &p.resmap, &res_bar[nb], (gcol + PARTS * UW) >> gsh, cw, ch, cn);
                         } else if (c + 1 < NC) {
                             mbar_expect_tx(&res_bar[nb], res_bytes);
-                            tma_load_4d(pbuf0 + nb * 2048, &p.resmap, &res_bar[nb], (gcol0 + BNC + half * UW) >> gsh, cw, ch, cn);
+                            tma_load_4d(pbuf0 + nb * 2048, &p.resmap, &res_bar[nb], (gcol0 + BNC + part * UW) >> gsh, cw, ch, cn);
                         } else if (has_next) {
                             mbar_expect_tx(&res_bar[nb], res_bytes);
-                            tma_load_4d(pbuf0 + nb * 2048, &p.resmap, &res_bar[nb], (n_tile2 * Cfg::N_TILE + half * UW) >> gsh,
+                            tma_load_4d(pbuf0 + nb * 2048, &p.resmap, &res_bar[nb], (n_tile2 * Cfg::N_TILE + part * UW) >> gsh,
                                         cw2, ch2, cn2);
                         }
                     }
@@ -236,6 +241,7 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
                     uint32_t vg[16];
                     tmem_ld16(taddr + u * UW + 16, vg);
                     tmem_ld_wait();
+                    uint32_t pk[8];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
@@ -247,11 +253,21 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
                         const float y1 = fmaf(__uint_as_float(va[4 * j + 1]), scale, ba.y) * gelu_fast_f(fmaf(__uint_as_float(vg[4 * j + 1]), scale, bg.y));
                         const float y2 = fmaf(__uint_as_float(va[4 * j + 2]), scale, ba.z) * gelu_fast_f(fmaf(__uint_as_float(vg[4 * j + 2]), scale, bg.z));
                         const float y3 = fmaf(__uint_as_float(va[4 * j + 3]), scale, ba.w) * gelu_fast_f(fmaf(__uint_as_float(vg[4 * j + 3]), scale, bg.w));
-                        *reinterpret_cast<uint2*>(pb + ho + j * 8) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                        pk[2 * j] = pack_bf16x2(y0, y1); pk[2 * j + 1] = pack_bf16x2(y2, y3);
                     }
+                    *reinterpret_cast<uint4*>(pb + ho + (hsw << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(pb + ho + ((hsw ^ 1) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 } else {
                     tmem_ld_wait();
                     if (has_res) mbar_wait(&res_bar[buf], (A / NBUF) & 1);
+                    // bf16 boxes are [32 rows][32 B] with the SWIZZLE_32B pattern (16-byte halves of rows 4..7, 12..15, ..
+                    // swapped): two conflict-free 16-byte accesses per row
+                    uint32_t pk[8], rb[8];
+                    if (!prim_f32 && has_res) {
+                        const uint4 r0 = *reinterpret_cast<const uint4*>(pb + ho + (hsw << 4));
+                        const uint4 r1 = *reinterpret_cast<const uint4*>(pb + ho + ((hsw ^ 1) << 4));
+                        rb[0] = r0.x; rb[1] = r0.y; rb[2] = r0.z; rb[3] = r0.w; rb[4] = r1.x; rb[5] = r1.y; rb[6] = r1.z; rb[7] = r1.w;
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float y0 = __uint_as_float(va[4 * j]) * scale, y1 = __uint_as_float(va[4 * j + 1]) * scale;
@@ -273,17 +289,20 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
                             if (has_res) { const float4 r = *slot4; y0 += r.x; y1 += r.y; y2 += r.z; y3 += r.w; }
                             if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
                             if (prim_store) *slot4 = make_float4(y0, y1, y2, y3);
-                            if (sec_store) *reinterpret_cast<uint2*>(hb + ho + j * 8) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                            if (sec_store) { pk[2 * j] = pack_bf16x2(y0, y1); pk[2 * j + 1] = pack_bf16x2(y2, y3); }
                         } else {
-                            uint2* const slot2 = reinterpret_cast<uint2*>(pb + ho + j * 8);
                             if (has_res) {
-                                const uint2 r = *slot2;
-                                const float2 f0 = unpack_bf16x2(r.x), f1 = unpack_bf16x2(r.y);
+                                const float2 f0 = unpack_bf16x2(rb[2 * j]), f1 = unpack_bf16x2(rb[2 * j + 1]);
                                 y0 += f0.x; y1 += f0.y; y2 += f1.x; y3 += f1.y;
                             }
                             if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-                            *slot2 = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                            pk[2 * j] = pack_bf16x2(y0, y1); pk[2 * j + 1] = pack_bf16x2(y2, y3);
                         }
+                    }
+                    if (!prim_f32 || sec_store) {
+                        uint8_t* const bb = prim_f32 ? hb : pb;
+                        *reinterpret_cast<uint4*>(bb + ho + (hsw << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(bb + ho + ((hsw ^ 1) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     }
                 }
                 // ---- hand the finished box(es) to the TMA engine
@@ -307,10 +326,10 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
     __syncwarp();
 }
 
-template <int BNC, int NC>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+template <int BNC, int NC, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((EW + 2) * 32, 1)
 conv_gemm_kernel(const __grid_constant__ GemmParams p) {
-    using Cfg = GemmCfg<BNC, NC>;
+    using Cfg = GemmCfg<BNC, NC, EW>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operand tiles need 1024-byte alignment; both CTAs of the pair compute the same offset
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -320,7 +339,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     uint64_t* acc_full = empty_bar + Cfg::STAGES;
     uint64_t* acc_empty = acc_full + Cfg::SLOTS;                                       // leader's are the live ones
     uint64_t* res_bar = acc_empty + Cfg::SLOTS;                                        // [epilogue warp][NBUF]
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps * Cfg::NBUF);
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(res_bar + EW * Cfg::NBUF);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -334,8 +353,8 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < Cfg::SLOTS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * kEpiWarps); }
-        for (int s = 0; s < kEpiWarps * Cfg::NBUF; ++s) mbar_init(&res_bar[s], 1);
+        for (int s = 0; s < Cfg::SLOTS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * EW); }
+        for (int s = 0; s < EW * Cfg::NBUF; ++s) mbar_init(&res_bar[s], 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_pair(tmem_base_smem, Cfg::TMEM_COLS);
@@ -424,7 +443,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     } else {
         // ===================================================================== epilogue (both CTAs, own 128 rows)
         if (p.epi_tma) {
-#define RG_EPI_CASE(M) case (M): epilogue_tma<BNC, NC, (M)>(p, staging, acc_full, acc_empty, res_bar, tmem_base, rank, cluster_id, n_clusters, warp, lane); break;
+#define RG_EPI_CASE(M) case (M): epilogue_tma<BNC, NC, EW, (M)>(p, staging, acc_full, acc_empty, res_bar, tmem_base, rank, cluster_id, n_clusters, warp, lane); break;
             switch (p.epi_mode) {
                 RG_EPI_CASE(EPI_PRIM_STORE)                                                   // bf16 out (q|k|v, q)
                 RG_EPI_CASE(EPI_PRIM_STORE | EPI_BIAS)                                        // bf16 out + bias
@@ -436,12 +455,13 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
                 RG_EPI_CASE(EPI_PRIM_F32 | EPI_PRIM_STORE | EPI_SEC_STORE | EPI_BIAS | EPI_RES)  // conv2 / proj_out with a bf16 copy
                 RG_EPI_CASE(EPI_PRIM_F32 | EPI_SEC_STORE | EPI_BIAS | EPI_RES)                // feed-forward out: fp32 residual, bf16 out
                 RG_EPI_CASE(EPI_GEGLU | EPI_PRIM_STORE | EPI_BIAS)                            // GEGLU
-                default: epilogue_tma<BNC, NC, EPI_GENERIC>(p, staging, acc_full, acc_empty, res_bar, tmem_base, rank, cluster_id, n_clusters, warp, lane); break;
+                default: epilogue_tma<BNC, NC, EW, EPI_GENERIC>(p, staging, acc_full, acc_empty, res_bar, tmem_base, rank, cluster_id, n_clusters, warp, lane); break;
             }
 #undef RG_EPI_CASE
         } else {
             const int q = warp & 3;                    // TMEM lane quarter this warp may access
-            const int half = (warp - 2) >> 2;          // units are dealt alternately to the two warps of a quarter
+            const int half = (warp - 2) >> 2;          // units are dealt round-robin to the warps of a quarter
+            constexpr int PARTS = Cfg::PARTS;
             const int rsub = lane >> 2, quad = lane & 3;
             float4* st0 = reinterpret_cast<float4*>(staging + (warp - 2) * Cfg::WARP_STAGING);
             float4* st1 = st0 + 128;
@@ -483,7 +503,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
                     if (geglu) {
                         // unit = 16 value columns followed by their 16 gate columns (host interleave, weights.interleave_geglu)
     #pragma unroll 1
-                        for (int u = half; u < BNC / 32; u += 2) {
+                        for (int u = half; u < BNC / 32; u += PARTS) {
                             if (ncol0 + u * 32 >= p.Cout) break;             // warp-uniform: the rest of the chunk is padding
                             uint32_t va[16], vg[16];
                             tmem_ld16(taddr + u * 32, va);
@@ -523,7 +543,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
                     } else {
                         int ub = 0;                              // staging buffer toggle: one __syncwarp per unit suffices
     #pragma unroll 1
-                        for (int u = half; u < BNC / 16; u += 2, ub ^= 1) {
+                        for (int u = half; u < BNC / 16; u += PARTS, ub ^= 1) {
                             const int col = ncol0 + u * 16 + quad * 4;
                             if (ncol0 + u * 16 >= p.Cout) break;             // warp-uniform: the rest of the chunk is padding
                             uint32_t v[16];
@@ -633,12 +653,12 @@ static int encode_act_map(CUtensorMap* m, const void* base, int C, long long W, 
                              CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BNC, int NC>
+template <int BNC, int NC, int EW = 8>
 static int launch_gemm(GemmParams& gp, const void* w, long long ktot, long long w_ld, cudaStream_t stream) {
-    using Cfg = GemmCfg<BNC, NC>;
+    using Cfg = GemmCfg<BNC, NC, EW>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BNC, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BNC, NC, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_gemm_kernel)");
         attr_done = true;
@@ -657,7 +677,7 @@ static int launch_gemm(GemmParams& gp, const void* w, long long ktot, long long 
     const int total = gp.n_pairs_m * gp.n_tiles_n * gp.ksplit;
     const int max_clusters = sm_count() / 2;
     const int clusters = total < max_clusters ? total : max_clusters;
-    conv_gemm_kernel<BNC, NC><<<2 * clusters, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(gp);
+    conv_gemm_kernel<BNC, NC, EW><<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(gp);
     count_launch();
     return check_launch("conv_gemm_kernel");
 }
@@ -789,7 +809,7 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
                 cuuint32_t box[4] = {16, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
                 cuuint32_t estr[4] = {1, 1, 1, 1};
                 return encode_tensor_map(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base,
-                                         dims, strides, box, estr, f32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+                                         dims, strides, box, estr, f32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
             };
             const void* pout = prim_f32 ? (const void*)c->out_f32 : (const void*)c->out_bf16;
             if (gp.prim_store && (rc = enc(&gp.pmap, pout, prim_f32))) return rc;
@@ -842,6 +862,9 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
         if (min_kblk < 0) { const char* e = getenv("RG_GEMM_NC2_MIN_KBLK"); min_kblk = e ? atoi(e) : 24; }
         if (Cout % 320 == 0 && gp.total_kblk > min_kblk && (long long)waves(320) * 865 <= (long long)waves(160) * 625)
             return launch_gemm<160, 2>(gp, c->w, ktot, w_ld, stream);
+        static int ew16 = -1;
+        if (ew16 < 0) { const char* e = getenv("RG_GEMM_EW16_MAX_KBLK"); ew16 = e ? atoi(e) : 24; }
+        if (gp.epi_tma && gp.total_kblk <= ew16) return launch_gemm<160, 1, 16>(gp, c->w, ktot, w_ld, stream);
         return launch_gemm<160, 1>(gp, c->w, ktot, w_ld, stream);
     }
     if (Cout > 128) return launch_gemm<256, 1>(gp, c->w, ktot, w_ld, stream);
