@@ -157,6 +157,11 @@ def run_b200(args) -> int:
         return 2
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # the contract is ONE JSON line on stdout: libraries that chat on stdout (NCCL prints its version banner there when
+    # NCCL_DEBUG=VERSION is set on the box) are sent to stderr until the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -216,6 +221,9 @@ def run_b200(args) -> int:
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if rank != 0:
         return 0
     total = BATCH * world
