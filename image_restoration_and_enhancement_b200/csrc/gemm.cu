@@ -18,10 +18,15 @@
 //   commits are multicast to both CTAs), warps 2..9 = epilogue of the CTA's own 128 accumulator rows.
 // * The accumulator chunks live in a ring of TMEM slots, so the epilogue of tile i overlaps the main loop of
 //   tile i+1 (fully for NC = 1, from the second chunk on for the 2 x 160 tile that uses 3 slots).
-// * Epilogue: TMEM -> registers -> per-warp shared-memory transpose -> row-contiguous global accesses (every
-//   warp instruction touches 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes), fusing scale, bias,
-//   per-image bias (time embedding), residual add (bf16 or fp32), SiLU, GEGLU (a * gelu(g)) and the bf16 and/or
-//   fp32 stores with arbitrary output pixel strides.
+// * Epilogue (epilogue_tma below): every epilogue warp owns 32 accumulator rows and walks 16-column units --
+//   residual box prefetched by TMA, tcgen05.ld, combine in shared memory in place (scale, bias, per-image bias,
+//   residual, SiLU / GEGLU), TMA store of the fp32 and / or bf16 box; unit code specialised per epilogue mode at
+//   compile time.  Outputs TMA cannot address (Cout = 3 fp32, unaligned pitches) take the direct epilogue: TMEM ->
+//   registers -> per-warp shared-memory transpose -> row-contiguous global accesses.
+// * Few-pixel levels with a long K (8x8 and below) run split-K x2: both halves are reduce-added by TMA into the
+//   zeroed fp32 output (x + y is commutative: bitwise reproducible), decided per image so results stay batch-invariant.
+// What bounds it (measured): all traffic through L2 -- operand fetches AND epilogue boxes --
+// shares about 6300 B/clk chip-wide; the short-K GEMMs of the transformer blocks sit on that limit, not on the MMA.
 #include <stdlib.h>
 #include "common.cuh"
 #include "internal.h"
