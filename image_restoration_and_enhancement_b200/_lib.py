@@ -12,7 +12,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "librestoragen.so"
 
 RG_ACT_NONE, RG_ACT_SILU, RG_ACT_GEGLU = 0, 1, 2
-RG_DT_BF16, RG_DT_F32 = 0, 1
+RG_DT_BF16, RG_DT_F32, RG_DT_F16 = 0, 1, 2
 
 
 class RgAct(C.Structure):
@@ -27,7 +27,7 @@ class RgConv(C.Structure):
                 ("bias", C.c_void_p), ("bias_n", C.c_void_p), ("bias_n_ld", C.c_int64), ("res", C.c_void_p), ("res_dtype", C.c_int32),
                 ("out_bf16", C.c_void_p), ("out_f32", C.c_void_p),
                 ("out_stride_n", C.c_int64), ("out_stride_h", C.c_int64), ("out_stride_w", C.c_int64),
-                ("act", C.c_int32), ("scale", C.c_float)]
+                ("act", C.c_int32), ("scale", C.c_float), ("out16_dtype", C.c_int32)]
 
 
 class RgAttn(C.Structure):
@@ -37,7 +37,7 @@ class RgAttn(C.Structure):
                 ("k_stride_b", C.c_int64), ("k_stride_t", C.c_int64), ("k_stride_h", C.c_int64),
                 ("v_stride_b", C.c_int64), ("v_stride_t", C.c_int64), ("v_stride_h", C.c_int64),
                 ("o_stride_b", C.c_int64), ("o_stride_t", C.c_int64), ("o_stride_h", C.c_int64),
-                ("scale", C.c_float)]
+                ("scale", C.c_float), ("dtype", C.c_int32)]
 
 
 class RgGn(C.Structure):

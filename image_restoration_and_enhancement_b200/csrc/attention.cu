@@ -17,6 +17,11 @@
 // straight from TMEM (no shared-memory round trip, no swizzled stores).  O accumulates in TMEM across the whole
 // key loop; the running maximum is only raised when a tile exceeds it by more than 2^8 (lazy rescale), in which
 // case the owning warp waits for the previous P V to retire and rescales its O rows in TMEM before publishing P.  exp is ex2.approx on pre-scaled logits.
+// fp16 operands (F16; what the UNet uses, like the reference's CUDA dtype): ex2.approx.f16x2 on the packed, pre-scaled
+// logits writes P directly as fp16 pairs (same MUFU rate as fp32 -- 16 ex2 / clk / SM measured either way -- but no
+// separate pack or row-sum instructions), and the softmax denominator is not summed by the threads at all -- the MMA
+// warp writes a column of ones into the zero padding of every V tile (column d of DV), so O_t[:, d] = sum_k P and it is
+// rescaled together with the rest of O_t.  bf16 operands keep the one-exponential-per-instruction fp32 path.
 // Head dims that are not a multiple of 64 (40, 80, 160 in SD-1.5) are handled by the TMA engine: the tensor
 // map's innermost extent is d, so the rest of each 64-wide box is zero-filled in shared memory.
 // V is consumed directly as an MN-major B operand -- no transpose anywhere.
@@ -49,7 +54,7 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
     return y;
 }
 
-template <int DKA, int DV, int BKV, int SBUF, bool PSEP, int STAGES>
+template <int DKA, int DQK, int DV, int BKV, int SBUF, bool PSEP, int STAGES, bool F16>
 struct AttnCfg {
     static constexpr int Q_TILE_BYTES = DKA * 128 * 128;           // one 128-query tile: DKA atoms of [128][64] bf16
     static constexpr int KV_ATOM_BYTES = BKV * 128;
@@ -82,9 +87,9 @@ constexpr float kLazyRescale = 8.0f;       // raise the running max only when a 
 
 // All barrier phases are indexed by the CTA-global key-tile counter G = (items done) * n_kv + j, which is also the
 // K/V ring position; score buffer G % SBUF is used for the (G / SBUF)-th time.
-template <int DKA, int DV, int BKV, int SBUF, bool PSEP, int STAGES>
+template <int DKA, int DQK, int DV, int BKV, int SBUF, bool PSEP, int STAGES, bool F16>
 __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
-    using Cfg = AttnCfg<DKA, DV, BKV, SBUF, PSEP, STAGES>;
+    using Cfg = AttnCfg<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16>;
     extern __shared__ __align__(16) uint8_t smem[];                    // window-relative base 0: no static smem
     if ((smem_u32(smem) & 1023u) != 0) __trap();                       // SWIZZLE_128B tiles need 1024-B alignment
     uint8_t* sQ = smem;                                                // [tile][atom][128][64]
@@ -146,14 +151,27 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
             }
         }
     } else if (warp == 9) {
-        // ===================================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);    // Q (K-major smem) x K (K-major smem)
-            constexpr uint32_t idesc_o = umma_idesc_bf16(128, DV, 0, 1);     // P (TMEM)         x V (MN-major smem)
+        // ===================================================================== MMA issuer (lane 0 issues; the whole
+        // warp waits on the barriers and, for fp16, patches the ones column into each freshly landed V tile)
+        {
+            // kind::f16 operand format: bits [7,10) A, [10,13) B: 0 = fp16, 1 = bf16
+            constexpr uint32_t fmt_clear = F16 ? ~((7u << 7) | (7u << 10)) : ~0u;
+            constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0) & fmt_clear;    // Q (K-major smem) x K (K-major smem)
+            constexpr uint32_t idesc_o = umma_idesc_bf16(128, DV, 0, 1) & fmt_clear;     // P (TMEM)         x V (MN-major smem)
             const uint32_t sq = smem_u32(sQ);
             const uint32_t skv = smem_u32(sKV);
             auto wait_kv = [&](uint32_t G) {
                 mbar_wait(&kv_full[G % STAGES], (G / STAGES) & 1);
+                if constexpr (F16) {
+                    // V[k][d] = 1 for every key row k: column d sits in the TMA zero padding (atom d / 64, 16-byte chunk
+                    // (d % 64) / 8 of the 128-byte row, SWIZZLE_128B: chunk ^= row & 7)
+                    uint8_t* sv = sKV + (G % STAGES) * Cfg::STAGE_BYTES + Cfg::K_BYTES + (p.d >> 6) * Cfg::KV_ATOM_BYTES;
+                    const int chunk = (p.d & 63) >> 3;
+                    for (int k = lane; k < BKV; k += 32)
+                        *reinterpret_cast<uint16_t*>(sv + k * 128 + ((chunk ^ (k & 7)) << 4)) = 0x3C00;   // fp16 1.0
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                }
                 tc_fence_after();
             };
             // S_t(G) = Q_t K_G^T
@@ -164,13 +182,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                     tc_fence_after();
                 }
                 const uint32_t sk = skv + (G % STAGES) * Cfg::STAGE_BYTES;
+                if (lane == 0) {
 #pragma unroll
-                for (int ks = 0; ks < DV / 16; ++ks) {           // columns >= d are zero in both operands
-                    const uint64_t adesc = umma_desc_kmajor_sw128(sq + t * Cfg::Q_TILE_BYTES + (ks / 4) * 128 * 128 + (ks % 4) * 32);
-                    const uint64_t bdesc = umma_desc_kmajor_sw128(sk + (ks / 4) * Cfg::KV_ATOM_BYTES + (ks % 4) * 32);
-                    umma_bf16(tmem_base + (t * SBUF + buf) * BKV, adesc, bdesc, idesc_s, ks != 0 ? 1u : 0u);
+                    for (int ks = 0; ks < DQK / 16; ++ks) {      // columns >= d are zero in both operands
+                        const uint64_t adesc = umma_desc_kmajor_sw128(sq + t * Cfg::Q_TILE_BYTES + (ks / 4) * 128 * 128 + (ks % 4) * 32);
+                        const uint64_t bdesc = umma_desc_kmajor_sw128(sk + (ks / 4) * Cfg::KV_ATOM_BYTES + (ks % 4) * 32);
+                        umma_bf16(tmem_base + (t * SBUF + buf) * BKV, adesc, bdesc, idesc_s, ks != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&s_full[t * SBUF + buf]);
                 }
-                umma_commit(&s_full[t * SBUF + buf]);
+                __syncwarp();
             };
             // O_t (+)= P_t(G) V_G
             auto issue_pv = [&](int t, uint32_t G, uint32_t acc) {
@@ -178,16 +199,20 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                 tc_fence_after();
                 const uint32_t sv = skv + (G % STAGES) * Cfg::STAGE_BYTES + Cfg::K_BYTES;
                 const uint32_t p_tmem = PSEP ? tmem_base + Cfg::P_COL + t * Cfg::P_STRIDE : tmem_base + t * BKV;
+                if (lane == 0) {
 #pragma unroll
-                for (int ks = 0; ks < BKV / 16; ++ks) {
-                    // 16 kv rows per k-step = 2 groups of 8 rows (1024 B each); 64-wide d blocks are KV_ATOM_BYTES apart
-                    const uint64_t bdesc = umma_desc_mnmajor_sw128(sv + ks * 2048, Cfg::KV_ATOM_BYTES, 1024);
-                    // P: two bf16 per 32-bit TMEM column -> 16 keys = 8 columns
-                    umma_bf16_ts(tmem_base + Cfg::O_COL + t * Cfg::O_STRIDE, p_tmem + ks * 8, bdesc, idesc_o,
-                                 (acc | (uint32_t)ks) != 0 ? 1u : 0u);
+                    for (int ks = 0; ks < BKV / 16; ++ks) {
+                        // 16 kv rows per k-step = 2 groups of 8 rows (1024 B each); 64-wide d blocks are KV_ATOM_BYTES apart
+                        const uint64_t bdesc = umma_desc_mnmajor_sw128(sv + ks * 2048, Cfg::KV_ATOM_BYTES, 1024);
+                        // P: two 16-bit values per 32-bit TMEM column -> 16 keys = 8 columns
+                        umma_bf16_ts(tmem_base + Cfg::O_COL + t * Cfg::O_STRIDE, p_tmem + ks * 8, bdesc, idesc_o,
+                                     (acc | (uint32_t)ks) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&pv_done[t]);
                 }
-                umma_commit(&pv_done[t]);
+                __syncwarp();
             };
+            auto commit = [&](uint64_t* bar) { if (lane == 0) umma_commit(bar); __syncwarp(); };
             uint32_t g0 = 0, it = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it, g0 += n_kv) {
                 mbar_wait(&q_full, it & 1);
@@ -195,17 +220,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                 if constexpr (!PSEP) {
                     wait_kv(g0);
                     issue_s(0, g0); issue_s(1, g0);
-                    if (n_kv == 1) umma_commit(&q_empty);
+                    if (n_kv == 1) commit(&q_empty);
                     for (int j = 0; j < n_kv; ++j) {
                         const uint32_t G = g0 + j;
 #pragma unroll
                         for (int t = 0; t < 2; ++t) {
                             issue_pv(t, G, j > 0 ? 1u : 0u);
-                            if (t == 1) umma_commit(&kv_empty[G % STAGES]);   // K_G / V_G consumed once these retire
+                            if (t == 1) commit(&kv_empty[G % STAGES]);   // K_G / V_G consumed once these retire
                             if (j + 1 < n_kv) {                               // in order behind P_t(G) V: P aliases S_t
                                 if (t == 0) wait_kv(G + 1);
                                 issue_s(t, G + 1);
-                                if (t == 1 && j + 2 == n_kv) umma_commit(&q_empty);
+                                if (t == 1 && j + 2 == n_kv) commit(&q_empty);
                             }
                         }
                     }
@@ -213,18 +238,18 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                     for (int j = 0; j < SBUF && j < n_kv; ++j) {              // SBUF score tiles of look-ahead
                         wait_kv(g0 + j);
                         issue_s(0, g0 + j); issue_s(1, g0 + j);
-                        if (j + 1 == n_kv) umma_commit(&q_empty);
+                        if (j + 1 == n_kv) commit(&q_empty);
                     }
                     for (int j = 0; j < n_kv; ++j) {
                         const uint32_t G = g0 + j;
                         if (j + SBUF < n_kv) {
                             wait_kv(G + SBUF);
                             issue_s(0, G + SBUF); issue_s(1, G + SBUF);
-                            if (j + SBUF + 1 == n_kv) umma_commit(&q_empty);
+                            if (j + SBUF + 1 == n_kv) commit(&q_empty);
                         }
                         issue_pv(0, G, j > 0 ? 1u : 0u);
                         issue_pv(1, G, j > 0 ? 1u : 0u);
-                        umma_commit(&kv_empty[G % STAGES]);
+                        commit(&kv_empty[G % STAGES]);
                     }
                 }
             }
@@ -310,17 +335,30 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                 const float neg_m = -m_run;
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
                 uint32_t pk[BKV / 2];
+                if constexpr (F16) {
+                    // two exponentials per MUFU instruction on the packed logits; the row sum comes out of the P V GEMM
 #pragma unroll
-                for (int i = 0; i < BKV; i += 4) {
-                    const float e0 = ex2_approx(fmaf(s[i], sl, neg_m));
-                    const float e1 = ex2_approx(fmaf(s[i + 1], sl, neg_m));
-                    const float e2 = ex2_approx(fmaf(s[i + 2], sl, neg_m));
-                    const float e3 = ex2_approx(fmaf(s[i + 3], sl, neg_m));
-                    l0 += e0; l1 += e1; l2 += e2; l3 += e3;
-                    pk[i / 2] = pack_bf16x2(e0, e1);
-                    pk[i / 2 + 1] = pack_bf16x2(e2, e3);
-                    if (!PSEP && (i & 31) == 28)                 // aliased: stream each finished 32-key chunk out
-                        tmem_st16(p_tmem + (i - 28) / 2, reinterpret_cast<uint32_t (&)[16]>(pk[(i - 28) / 2]));
+                    for (int i = 0; i < BKV; i += 2) {
+                        const float x0 = fmaf(s[i], sl, neg_m), x1 = fmaf(s[i + 1], sl, neg_m);
+                        uint32_t h;
+                        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+                        asm("ex2.approx.f16x2 %0, %1;" : "=r"(pk[i / 2]) : "r"(h));
+                        if (!PSEP && (i & 31) == 30)             // aliased: stream each finished 32-key chunk out
+                            tmem_st16(p_tmem + (i - 30) / 2, reinterpret_cast<uint32_t (&)[16]>(pk[(i - 30) / 2]));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < BKV; i += 4) {
+                        const float e0 = ex2_approx(fmaf(s[i], sl, neg_m));
+                        const float e1 = ex2_approx(fmaf(s[i + 1], sl, neg_m));
+                        const float e2 = ex2_approx(fmaf(s[i + 2], sl, neg_m));
+                        const float e3 = ex2_approx(fmaf(s[i + 3], sl, neg_m));
+                        l0 += e0; l1 += e1; l2 += e2; l3 += e3;
+                        pk[i / 2] = pack_bf16x2(e0, e1);
+                        pk[i / 2 + 1] = pack_bf16x2(e2, e3);
+                        if (!PSEP && (i & 31) == 28)             // aliased: stream each finished 32-key chunk out
+                            tmem_st16(p_tmem + (i - 28) / 2, reinterpret_cast<uint32_t (&)[16]>(pk[(i - 28) / 2]));
+                    }
                 }
                 RG_STAMP(4);
                 if constexpr (PSEP) {
@@ -340,7 +378,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
             mbar_wait(&pv_done[t], (g0 + n_kv - 1) & 1);
             tc_fence_after();
             const int tq = qp * 256 + t * 128 + row;
-            const float inv = 1.0f / l_run;
+            float l_tot = l_run;
+            if constexpr (F16) {                                 // the ones column of V: O_t[:, d] = sum_k P
+                uint32_t v[16];
+                tmem_ld16(o_tmem + (p.d & ~15), v);
+                tmem_ld_wait();
+                l_tot = __uint_as_float(v[0]);
+#pragma unroll
+                for (int i = 1; i < 16; ++i) if ((p.d & 15) == i) l_tot = __uint_as_float(v[i]);
+            }
+            const float inv = 1.0f / l_tot;
             __nv_bfloat16* dst = p.out + (long long)b * p.osb + (long long)tq * p.ost + (long long)h * p.osh;
 #pragma unroll
             for (int c = 0; c < DV; c += 16) {
@@ -380,12 +427,12 @@ static int encode_qkv_map(CUtensorMap* m, const void* base, int d, int heads, lo
                              CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int DKA, int DV, int BKV, int SBUF, bool PSEP, int STAGES>
+template <int DKA, int DQK, int DV, int BKV, int SBUF, bool PSEP, int STAGES, bool F16>
 static int launch_attn(const rg_attn_t* a, cudaStream_t stream) {
-    using Cfg = AttnCfg<DKA, DV, BKV, SBUF, PSEP, STAGES>;
+    using Cfg = AttnCfg<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(attention_kernel<DKA, DV, BKV, SBUF, PSEP, STAGES>,
+        cudaError_t e = cudaFuncSetAttribute(attention_kernel<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attention_kernel)");
         attr_done = true;
@@ -407,7 +454,7 @@ static int launch_attn(const rg_attn_t* a, cudaStream_t stream) {
     p.scale_log2 = a->scale * 1.4426950408889634f;
     p.trace = g_attn_trace;
     const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
-    attention_kernel<DKA, DV, BKV, SBUF, PSEP, STAGES><<<grid, kAttnThreads, Cfg::SMEM_BYTES, stream>>>(p);
+    attention_kernel<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16><<<grid, kAttnThreads, Cfg::SMEM_BYTES, stream>>>(p);
     count_launch();
     return check_launch("attention_kernel");
 }
@@ -434,9 +481,18 @@ extern "C" int rg_attention(const rg_attn_t* a, rg_stream_t stream_) {
          reinterpret_cast<uintptr_t>(a->out)) & 15)
         return set_error(RG_ERR_ARG, "attention: pointers must be 16-byte aligned");
     const int dv = (a->d + 15) / 16 * 16;
-    if (dv <= 48) return launch_attn<1, 48, 128, 1, true, 4>(a, stream);
-    if (dv <= 64) return launch_attn<1, 64, 128, 1, true, 4>(a, stream);
-    if (dv <= 80) return launch_attn<2, 80, 128, 1, false, 2>(a, stream);
-    if (dv <= 128) return launch_attn<2, 128, 128, 1, false, 2>(a, stream);
-    return launch_attn<3, 160, 64, 1, false, 2>(a, stream);
+    // template arguments: DKA (64-wide atoms of d), DQK (k extent of Q K^T), DV (n extent of P V), BKV, SBUF, PSEP, STAGES, F16
+    if (a->dtype == RG_DT_F16) {
+        // fp16 operands: DV includes the ones column at index d (inside the padding for d = 40, one more 16-column step else)
+        if (a->d == 40) return launch_attn<1, 48, 48, 128, 1, true, 4, true>(a, stream);
+        if (a->d == 80) return launch_attn<2, 80, 96, 128, 1, false, 2, true>(a, stream);
+        if (a->d == 160) return launch_attn<3, 160, 176, 64, 1, false, 2, true>(a, stream);
+        return set_error(RG_ERR_ARG, "attention: the fp16 path supports head dims 40, 80 and 160");
+    }
+    if (a->dtype != RG_DT_BF16) return set_error(RG_ERR_ARG, "attention: dtype must be RG_DT_BF16 or RG_DT_F16");
+    if (dv <= 48) return launch_attn<1, 48, 48, 128, 1, true, 4, false>(a, stream);
+    if (dv <= 64) return launch_attn<1, 64, 64, 128, 1, true, 4, false>(a, stream);
+    if (dv <= 80) return launch_attn<2, 80, 80, 128, 1, false, 2, false>(a, stream);
+    if (dv <= 128) return launch_attn<2, 128, 128, 128, 1, false, 2, false>(a, stream);
+    return launch_attn<3, 160, 160, 64, 1, false, 2, false>(a, stream);
 }

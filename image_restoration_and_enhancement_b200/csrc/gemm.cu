@@ -64,6 +64,7 @@ struct GemmParams {
     int ksplit, kper;                 // split-K: each tile covers k-blocks [ks*kper, (ks+1)*kper) and is reduce-added
     int epi_mode;                     // EPI_* bit set when it matches a specialised epilogue, else EPI_GENERIC
     int dbg;                          // RG_GEMM_DEBUG bits (perf experiments only): 1 skip units, 2 skip stores, 4 skip residual
+    int out_f16;                      // the 16-bit output is fp16 (attention operands), not bf16
     int out_cols;                     // Cout, or Cout / 2 for GEGLU
     CUtensorMap resmap, pmap, hmap;   // residual load, primary store, secondary (bf16) store
 };
@@ -121,7 +122,7 @@ struct RowGeom {
 // MODE: bit set of EPI_* known at compile time (straight-line unit code, four independent column groups in flight),
 // or EPI_GENERIC to read every flag from the parameters at run time.
 enum : int { EPI_GEGLU = 1, EPI_PRIM_F32 = 2, EPI_RES = 4, EPI_PRIM_STORE = 8, EPI_SEC_STORE = 16, EPI_BIAS = 32,
-             EPI_BIASN = 64, EPI_SILU = 128, EPI_SCALE = 256, EPI_GENERIC = 1 << 20 };
+             EPI_BIASN = 64, EPI_SILU = 128, EPI_SCALE = 256, EPI_F16 = 512, EPI_GENERIC = 1 << 20 };
 
 template <int BNC, int NC, int EW, int MODE>
 __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging, uint64_t* acc_full, uint64_t* acc_empty,
@@ -145,6 +146,8 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
     const float scale = (G || (MODE & EPI_SCALE)) ? p.scale : 1.0f;
     const float* const bias = (G || (MODE & EPI_BIAS)) ? p.bias : nullptr;
     const bool use_bn = G ? p.bias_n != nullptr : (MODE & EPI_BIASN) != 0;
+    const bool out_f16 = G ? p.out_f16 != 0 : (MODE & EPI_F16) != 0;
+    auto pack16 = [&](float lo, float hi) { return out_f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); };
     const int gsh = geglu ? 1 : 0;                        // output column = GEMM column >> gsh
     const int UW = geglu ? 32 : 16;                       // accumulator columns per unit
     const int UPC = BNC / UW;                             // units per chunk
@@ -258,7 +261,7 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
                         const float y1 = fmaf(__uint_as_float(va[4 * j + 1]), scale, ba.y) * gelu_fast_f(fmaf(__uint_as_float(vg[4 * j + 1]), scale, bg.y));
                         const float y2 = fmaf(__uint_as_float(va[4 * j + 2]), scale, ba.z) * gelu_fast_f(fmaf(__uint_as_float(vg[4 * j + 2]), scale, bg.z));
                         const float y3 = fmaf(__uint_as_float(va[4 * j + 3]), scale, ba.w) * gelu_fast_f(fmaf(__uint_as_float(vg[4 * j + 3]), scale, bg.w));
-                        pk[2 * j] = pack_bf16x2(y0, y1); pk[2 * j + 1] = pack_bf16x2(y2, y3);
+                        pk[2 * j] = pack16(y0, y1); pk[2 * j + 1] = pack16(y2, y3);
                     }
                     *reinterpret_cast<uint4*>(pb + ho + (hsw << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     *reinterpret_cast<uint4*>(pb + ho + ((hsw ^ 1) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -294,14 +297,14 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
                             if (has_res) { const float4 r = *slot4; y0 += r.x; y1 += r.y; y2 += r.z; y3 += r.w; }
                             if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
                             if (prim_store) *slot4 = make_float4(y0, y1, y2, y3);
-                            if (sec_store) { pk[2 * j] = pack_bf16x2(y0, y1); pk[2 * j + 1] = pack_bf16x2(y2, y3); }
+                            if (sec_store) { pk[2 * j] = pack16(y0, y1); pk[2 * j + 1] = pack16(y2, y3); }
                         } else {
                             if (has_res) {
                                 const float2 f0 = unpack_bf16x2(rb[2 * j]), f1 = unpack_bf16x2(rb[2 * j + 1]);
                                 y0 += f0.x; y1 += f0.y; y2 += f1.x; y3 += f1.y;
                             }
                             if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-                            pk[2 * j] = pack_bf16x2(y0, y1); pk[2 * j + 1] = pack_bf16x2(y2, y3);
+                            pk[2 * j] = pack16(y0, y1); pk[2 * j + 1] = pack16(y2, y3);
                         }
                     }
                     if (!prim_f32 || sec_store) {
@@ -450,7 +453,8 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         if (p.epi_tma) {
 #define RG_EPI_CASE(M) case (M): epilogue_tma<BNC, NC, EW, (M)>(p, staging, acc_full, acc_empty, res_bar, tmem_base, rank, cluster_id, n_clusters, warp, lane); break;
             switch (p.epi_mode) {
-                RG_EPI_CASE(EPI_PRIM_STORE)                                                   // bf16 out (q|k|v, q)
+                RG_EPI_CASE(EPI_PRIM_STORE)                                                   // bf16 out
+                RG_EPI_CASE(EPI_PRIM_STORE | EPI_F16)                                         // fp16 out (q|k|v, q)
                 RG_EPI_CASE(EPI_PRIM_STORE | EPI_BIAS)                                        // bf16 out + bias
                 RG_EPI_CASE(EPI_PRIM_STORE | EPI_BIAS | EPI_BIASN)                            // resnet conv1 (+ time embedding)
                 RG_EPI_CASE(EPI_PRIM_STORE | EPI_BIAS | EPI_RES)                              // VAE conv2: bf16 residual
@@ -540,7 +544,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
                                     const float y2 = (a.z * p.scale + ba.z) * gelu_fast_f(gt.z * p.scale + bg.z);
                                     const float y3 = (a.w * p.scale + ba.w) * gelu_fast_f(gt.w * p.scale + bg.w);
                                     *reinterpret_cast<uint2*>(p.out_bf16 + g.off[i] + co) =
-                                        make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                                        (p.out_f16 ? make_uint2(pack_f16x2(y0, y1), pack_f16x2(y2, y3)) : make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3)));
                                 }
                             }
                             __syncwarp();
@@ -599,7 +603,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
                                         if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + g.off[i] + col) = make_float4(y0, y1, y2, y3);
                                         if (p.out_bf16)
                                             *reinterpret_cast<uint2*>(p.out_bf16 + g.off[i] + col) =
-                                                make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                                                (p.out_f16 ? make_uint2(pack_f16x2(y0, y1), pack_f16x2(y2, y3)) : make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3)));
                                     }
                                 }
                             } else {
@@ -623,7 +627,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
                                                 }
                                                 y = apply_act(y, p.act);
                                                 if (p.out_f32) p.out_f32[g.off[i] + cidx] = y;
-                                                if (p.out_bf16) p.out_bf16[g.off[i] + cidx] = __float2bfloat16(y);
+                                                if (p.out_bf16) { if (p.out_f16) reinterpret_cast<__half*>(p.out_bf16)[g.off[i] + cidx] = __float2half_rn(y); else p.out_bf16[g.off[i] + cidx] = __float2bfloat16(y); }
                                             }
                                         }
                                     }
@@ -776,6 +780,9 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
     gp.out_f32 = c->out_f32;
     gp.osn = c->out_stride_n; gp.osh = c->out_stride_h; gp.osw = c->out_stride_w;
     gp.act = c->act; gp.scale = c->scale;
+    gp.out_f16 = c->out16_dtype == RG_DT_F16;
+    if (gp.out_f16 && (c->act == RG_ACT_GEGLU || (c->res && c->res_dtype == RG_DT_BF16)))
+        return set_error(RG_ERR_ARG, "rg_conv2d: fp16 output is for plain projections (no GEGLU, no bf16 residual)");
     const bool aligned = (c->out_stride_n % 8 == 0) && (c->out_stride_h % 8 == 0) && (c->out_stride_w % 8 == 0) &&
                          !(reinterpret_cast<uintptr_t>(c->out_bf16) & 15) && !(reinterpret_cast<uintptr_t>(c->out_f32) & 15) &&
                          !(reinterpret_cast<uintptr_t>(c->res) & 15) && !(reinterpret_cast<uintptr_t>(c->bias) & 15) &&
@@ -833,6 +840,7 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
             if (c->bias_n) mode |= 64;
             if (c->act == RG_ACT_SILU) mode |= 128;
             if (c->scale != 1.0f) mode |= 256;
+            if (c->out16_dtype == RG_DT_F16) mode |= 512;
             gp.epi_mode = gp.dbg ? (1 << 20) : mode;    // debug experiments run the generic (run-time flag) epilogue
         }
     }

@@ -13,10 +13,10 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (RG_ACT_GEGLU, RG_ACT_NONE, RG_ACT_SILU, RG_DT_BF16, RG_DT_F32, RgAct, RgAttn, RgConv, RgGn,
+from ._lib import (RG_ACT_GEGLU, RG_ACT_NONE, RG_ACT_SILU, RG_DT_BF16, RG_DT_F16, RG_DT_F32, RgAct, RgAttn, RgConv, RgGn,
                    RgSched, check)
 
-bf16, f32 = torch.bfloat16, torch.float32
+bf16, f32, f16 = torch.bfloat16, torch.float32, torch.float16
 GN_MAX_IMAGES = 1024      # RG_GN_MAX_IMAGES: fixed-size counter area in front of the GroupNorm workspace
 GN_MAX_BLOCKS = 64        # RG_GN_MAX_BLOCKS in include/restoragen.h
 
@@ -85,11 +85,13 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, *, kh: int = 1, kw: int = 1, stride
            pad_l: int = 0, OH: int | None = None, OW: int | None = None, x2: torch.Tensor | None = None,
            bias: torch.Tensor | None = None, bias_n: torch.Tensor | None = None, res: torch.Tensor | None = None,
            out_bf16: torch.Tensor | bool | None = None, out_f32: torch.Tensor | bool | None = None,
-           act: int = RG_ACT_NONE, scale: float = 1.0, out_strides: tuple | None = None, w_ld: int = 0):
+           act: int = RG_ACT_NONE, scale: float = 1.0, out_strides: tuple | None = None, w_ld: int = 0,
+           out_half: torch.dtype = bf16):
     """Implicit-GEMM convolution / linear (rg_conv2d).  ``x``: bf16 [N,H,W,C]; ``w``: bf16 [Cout, kh*kw*C (+C2)].
 
     ``out_bf16`` / ``out_f32``: True to allocate a contiguous [N,OH,OW,Cout'] output, or a tensor to write into
-    (with ``out_strides`` = element strides (n, h, w) when it is not contiguous).  Returns (out_bf16, out_f32).
+    (with ``out_strides`` = element strides (n, h, w) when it is not contiguous).  ``out_half``: element type of the
+    16-bit output (bf16, or fp16 for the attention operands).  Returns (out_bf16, out_f32).
     """
     lib = _lib.load()
     N, H, W, Cin = x.shape
@@ -102,7 +104,7 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, *, kh: int = 1, kw: int = 1, stride
         w_ld = w.stride(0)
     Cw = Cout // 2 if act == RG_ACT_GEGLU else Cout
     if out_bf16 is True:
-        out_bf16 = torch.empty((N, OH, OW, Cw), dtype=bf16, device=x.device)
+        out_bf16 = torch.empty((N, OH, OW, Cw), dtype=out_half, device=x.device)
     if out_f32 is True:
         out_f32 = torch.empty((N, OH, OW, Cw), dtype=f32, device=x.device)
     if out_bf16 is False:
@@ -127,8 +129,9 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, *, kh: int = 1, kw: int = 1, stride
     if res is not None:
         p.res, p.res_dtype = res.data_ptr(), _dt(res)
     if out_bf16 is not None:
-        assert out_bf16.dtype == bf16
+        assert out_bf16.dtype in (bf16, f16)
         p.out_bf16 = out_bf16.data_ptr()
+        p.out16_dtype = RG_DT_F16 if out_bf16.dtype == f16 else RG_DT_BF16
     if out_f32 is not None:
         assert out_f32.dtype == f32
         p.out_f32 = out_f32.data_ptr()
@@ -151,12 +154,12 @@ def linear(x: torch.Tensor, w: torch.Tensor, **kw):
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, out: torch.Tensor | None = None):
-    """q [B,Nq,H,d], k/v [B,Nk,H,d] bf16 views (d contiguous) -> out bf16 [B,Nq,H,d] contiguous."""
+    """q [B,Nq,H,d], k/v [B,Nk,H,d] bf16 or fp16 views (d contiguous) -> out bf16 [B,Nq,H,d] contiguous."""
     lib = _lib.load()
     B, Nq, Hh, d = q.shape
     Nk = k.shape[1]
     for t in (q, k, v):
-        assert t.dtype == bf16 and t.stride(3) == 1
+        assert t.dtype == q.dtype and t.dtype in (bf16, f16) and t.stride(3) == 1
     if out is None:
         out = torch.empty((B, Nq, Hh, d), dtype=bf16, device=q.device)
     p = RgAttn()
@@ -167,6 +170,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, o
     p.v_stride_b, p.v_stride_t, p.v_stride_h = v.stride(0), v.stride(1), v.stride(2)
     p.o_stride_b, p.o_stride_t, p.o_stride_h = out.stride(0), out.stride(1), out.stride(2)
     p.scale = scale
+    p.dtype = RG_DT_F16 if q.dtype == f16 else RG_DT_BF16
     e0 = _prof_begin()
     check(lib.rg_attention(C.byref(p), _stream()), "rg_attention")
     _prof_end(e0, 4.0 * B * Hh * Nq * Nk * d, "attention", f"B={B} H={Hh} Nq={Nq} Nk={Nk} d={d}")

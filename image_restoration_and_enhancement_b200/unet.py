@@ -22,7 +22,7 @@ from . import ops
 from ._lib import RG_ACT_GEGLU, RG_ACT_SILU
 from .weights import interleave_geglu, pack_conv, unet_param_shapes, upsample_parity_weights
 
-bf16, f32 = torch.bfloat16, torch.float32
+bf16, f32, f16 = torch.bfloat16, torch.float32, torch.float16
 
 
 class _Resnet:
@@ -64,7 +64,7 @@ class _Transformer:
         self.w_gg, self.b_gg = wg.to(dev, bf16).contiguous(), bg.to(dev, f32).contiguous()
         self.w_ff, self.b_ff = g(t + "ff.net.2.weight").to(dev, bf16).contiguous(), f(t + "ff.net.2.bias")
         self.C = self.w_in.shape[0]
-        self.kv = None            # cross-attention K/V of the current prompt batch: bf16 [Bu, 77, 2C]
+        self.kv = None            # cross-attention K/V of the current prompt batch: fp16 [Bu, 77, 2C]
         self.kv_bufs = {}         # persistent per batch size, so captured graphs keep valid addresses
 
 
@@ -142,7 +142,7 @@ class UNetB200:
         for t in self.transformers:
             buf = t.kv_bufs.get((Bu, T))
             if buf is None:
-                buf = t.kv_bufs[(Bu, T)] = torch.empty((Bu, T, 2 * t.C), dtype=bf16, device=self.device)
+                buf = t.kv_bufs[(Bu, T)] = torch.empty((Bu, T, 2 * t.C), dtype=f16, device=self.device)
             ops.linear(c, t.w_kv2, out_bf16=buf.view(1, 1, Bu * T, 2 * t.C))
             t.kv = buf
         self.ctx_batch = Bu
@@ -175,13 +175,13 @@ class UNetB200:
         tok = tok.view(M, Cc)
         # self-attention
         l1 = ops.layernorm(tok, *t.ln[0])
-        qkv, _ = ops.linear(l1, t.w_qkv, out_bf16=True)
+        qkv, _ = ops.linear(l1, t.w_qkv, out_bf16=True, out_half=f16)         # attention operands in fp16 (like the reference)
         qkv = qkv.view(N, H * W, 3, heads, d)
         o = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], d ** -0.5)
         ops.linear(o.view(M, Cc), t.w_o1, bias=t.b_o1, res=tok, out_f32=tok.view(1, 1, M, Cc))
         # cross-attention against the cached prompt K/V
         l2 = ops.layernorm(tok, *t.ln[1])
-        q2, _ = ops.linear(l2, t.w_q2, out_bf16=True)
+        q2, _ = ops.linear(l2, t.w_q2, out_bf16=True, out_half=f16)
         kv = t.kv.view(N, -1, 2, heads, d)
         o2 = ops.attention(q2.view(N, H * W, heads, d), kv[:, :, 0], kv[:, :, 1], d ** -0.5)
         ops.linear(o2.view(M, Cc), t.w_o2, bias=t.b_o2, res=tok, out_f32=tok.view(1, 1, M, Cc))

@@ -44,6 +44,7 @@ typedef void* rg_stream_t; /* cudaStream_t */
 
 #define RG_DT_BF16 0
 #define RG_DT_F32 1
+#define RG_DT_F16 2
 
 const char* rg_last_error(void);
 int rg_version(void);
@@ -89,6 +90,8 @@ typedef struct rg_conv {
     int64_t out_stride_n, out_stride_h, out_stride_w;
     int32_t act;           /* RG_ACT_* */
     float scale;
+    int32_t out16_dtype;   /* element type written through out_bf16: RG_DT_BF16 (default) or RG_DT_F16 (the attention
+                              operands q, k, v: fp16 like the reference's CUDA path, src/inference.py:57) */
 } rg_conv_t;
 
 int rg_conv2d(const rg_conv_t* p, rg_stream_t stream);
@@ -97,7 +100,9 @@ int rg_conv2d(const rg_conv_t* p, rg_stream_t stream);
  * K5/K6  fused flash-style attention on tcgen05: O = softmax(scale * Q K^T) V, no mask.
  *   replaces F.scaled_dot_product_attention in attn1 (self, N = H*W tokens) and attn2
  *   (cross, 77 CLIP tokens) of every BasicTransformerBlock.
- *   q/k/v/out are bf16 [B][tokens][heads][d] views with arbitrary (multiple-of-8) strides.
+ *   q/k/v are bf16 or fp16, out is bf16: [B][tokens][heads][d] views with arbitrary (multiple-of-8) strides.
+ *   The fp16 path (d in {40, 80, 160}) evaluates two exponentials per MUFU instruction (ex2.approx.f16x2) and takes
+ *   the softmax denominator from a ones column appended to V inside the P V GEMM.
  * ------------------------------------------------------------------------------------------- */
 typedef struct rg_attn {
     const void *q, *k, *v;
@@ -109,6 +114,7 @@ typedef struct rg_attn {
     int64_t v_stride_b, v_stride_t, v_stride_h;
     int64_t o_stride_b, o_stride_t, o_stride_h;
     float scale;
+    int32_t dtype;                 /* element type of q, k, v: RG_DT_BF16 (default) or RG_DT_F16; out is always bf16 */
 } rg_attn_t;
 
 int rg_attention(const rg_attn_t* p, rg_stream_t stream);

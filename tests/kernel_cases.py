@@ -149,18 +149,19 @@ def case_conv_strided_out(seed=29):
 
 
 # ------------------------------------------------------------------------------------------------ attention
-def case_attention(B=2, heads=8, d=40, Nq=1024, Nk=None, seed=20, fused_qkv=True):
+def case_attention(B=2, heads=8, d=40, Nq=1024, Nk=None, seed=20, fused_qkv=True, dtype=torch.bfloat16):
+    """``dtype`` fp16: the UNet's path (two exponentials per MUFU op, denominator from a ones column of V)."""
     _setup()
     Nk = Nq if Nk is None else Nk
     C = heads * d
     if fused_qkv and Nk == Nq:
-        qkv = _rand((B, Nq, 3 * C), seed)
+        qkv = _rand((B, Nq, 3 * C), seed, dtype=dtype)
         q = qkv[:, :, 0:C].unflatten(2, (heads, d))
         k = qkv[:, :, C:2 * C].unflatten(2, (heads, d))
         v = qkv[:, :, 2 * C:].unflatten(2, (heads, d))
     else:
-        q = _rand((B, Nq, heads, d), seed)
-        kv = _rand((B, Nk, 2 * C), seed + 1)
+        q = _rand((B, Nq, heads, d), seed, dtype=dtype)
+        kv = _rand((B, Nk, 2 * C), seed + 1, dtype=dtype)
         k = kv[:, :, :C].unflatten(2, (heads, d))
         v = kv[:, :, C:].unflatten(2, (heads, d))
     scale = d ** -0.5
@@ -169,6 +170,33 @@ def case_attention(B=2, heads=8, d=40, Nq=1024, Nk=None, seed=20, fused_qkv=True
     out = ops.attention(q, k, v, scale)
     torch.cuda.synchronize()
     return rel_l2(out, ref), TOL_ATTN
+
+
+def case_attention_large_logits(seed=47):
+    """fp16 path with logits spread over +-60 (log2 units): exercises the lazy rescale of O and of the ones column."""
+    _setup()
+    B, heads, d, N = 1, 8, 40, 1024
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    q = (torch.randn((B, N, heads, d), generator=g) * 3.0).to(torch.float16).to(DEV)
+    k = (torch.randn((B, N, heads, d), generator=g) * 3.0).to(torch.float16).to(DEV)
+    k[:, 700:] *= 2.0                                   # later key tiles dominate: the running max must be raised
+    v = torch.randn((B, N, heads, d), generator=g).to(torch.float16).to(DEV)
+    ref = F.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2),
+                                         v.float().transpose(1, 2)).transpose(1, 2)
+    out = ops.attention(q, k, v, d ** -0.5)
+    torch.cuda.synchronize()
+    return rel_l2(out, ref), TOL_ATTN
+
+
+def case_linear_f16(seed=48):
+    """q|k|v projection written as fp16 (16-bit output dtype flag of rg_conv2d)."""
+    _setup()
+    x = _rand((4096, 320), seed)
+    w = _rand((960, 320), seed + 1, 1.0 / math.sqrt(320))
+    ob, _ = ops.linear(x, w, out_bf16=True, out_half=torch.float16)
+    torch.cuda.synchronize()
+    assert ob.dtype == torch.float16
+    return rel_l2(ob, x.float() @ w.float().t()), 1e-3      # fp16 rounding: 2^-11
 
 
 # ------------------------------------------------------------------------------------------------ norms
@@ -363,6 +391,14 @@ CASES = {
     "attn_cross_d160": lambda: case_attention(B=2, heads=8, d=160, Nq=64, Nk=77, seed=26, fused_qkv=False),
     "attn_ragged": lambda: case_attention(B=1, heads=8, d=40, Nq=2542, seed=27),
     "attn_d64": lambda: case_attention(B=1, heads=4, d=64, Nq=300, seed=28),
+    "attn_f16_self_d40": lambda: case_attention(B=2, heads=8, d=40, Nq=4096, seed=41, dtype=torch.float16),
+    "attn_f16_self_d80": lambda: case_attention(B=2, heads=8, d=80, Nq=1024, seed=42, dtype=torch.float16),
+    "attn_f16_self_d160": lambda: case_attention(B=3, heads=8, d=160, Nq=256, seed=43, dtype=torch.float16),
+    "attn_f16_cross_d40": lambda: case_attention(B=2, heads=8, d=40, Nq=4096, Nk=77, seed=44, fused_qkv=False, dtype=torch.float16),
+    "attn_f16_cross_d160": lambda: case_attention(B=2, heads=8, d=160, Nq=64, Nk=77, seed=45, fused_qkv=False, dtype=torch.float16),
+    "attn_f16_ragged": lambda: case_attention(B=1, heads=8, d=80, Nq=651, seed=46, dtype=torch.float16),
+    "attn_f16_large_logits": lambda: case_attention_large_logits(),
+    "linear_f16_out": lambda: case_linear_f16(),
     "attn_d128": lambda: case_attention(B=1, heads=2, d=128, Nq=700, seed=29),
     "attn_many_items": lambda: case_attention(B=4, heads=8, d=40, Nq=2048, seed=30),       # > 148 items: persistent loop
     # --- norms
