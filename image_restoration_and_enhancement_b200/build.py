@@ -15,7 +15,7 @@ LIB = HERE / "librestoragen.so"
 STAMP = HERE / "build" / "stamp.txt"
 SOURCES = ["api.cu", "gemm.cu", "attention.cu", "norm.cu", "elementwise.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("RG_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:
