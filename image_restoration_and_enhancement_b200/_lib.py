@@ -82,6 +82,9 @@ SIGNATURES = {
     "rg_scale_f32": (C.c_int, [_p, _f32, _i64, _p, _p]),
     "rg_cast_f32_bf16": (C.c_int, [_p, _i64, _p, _p]),
     "rg_memset_zero": (C.c_int, [_p, _i64, _p]),
+    "rg_metrics_sse_u8": (C.c_int, [_p, _p, _i32, _i64, _p, _p]),
+    "rg_metrics_ssim_chunks": (C.c_int, [_i32, _i32]),
+    "rg_metrics_ssim_u8": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, C.c_double, C.c_double, C.c_double, _p, _p, _p]),
 }
 
 

@@ -8,6 +8,10 @@ contributes its per-image float64 values with their global indices, rank 0 reord
 the result is bit-identical to a single-process run (partial sums are never all-reduced).
 LPIPS needs pretrained AlexNet + linear heads that are not available offline: ``use_lpips`` is accepted for API
 parity and yields ``None`` values unless a callable is supplied.
+
+``psnr_ssim_device`` is the GPU metric pass (SURVEY 8f "f2"): the predictions never leave HBM, the kernels in
+``csrc/metrics.cu`` reproduce the float64 operation ORDER of scipy's uniform filter and numpy's mean, and the values
+returned are bit-identical to ``calculate_psnr`` / ``calculate_ssim`` (tests/test_kernels_gpu.py).
 """
 from __future__ import annotations
 
@@ -66,6 +70,52 @@ def ssim(gt: np.ndarray, pred: np.ndarray, data_range: float = 255.0, channel_ax
     for c in range(gt.shape[channel_axis]):
         vals[c] = _ssim_2d(np.take(gt, c, axis=channel_axis), np.take(pred, c, axis=channel_axis), data_range)
     return float(vals.mean())
+
+
+def psnr_ssim_device(pred, gt, data_range: float = 255.0, K1: float = 0.01, K2: float = 0.03):
+    """PSNR and SSIM of u8 image batches resident on the GPU: ``pred``, ``gt`` torch.uint8 CUDA tensors [N,H,W,C].
+    Returns two lists of Python floats, bit-identical to ``psnr(gt[i], pred[i])`` / ``ssim(gt[i], pred[i])``.
+    The scalar tails (mse -> dB, chunk sums -> mean) are the same numpy float64 expressions the CPU functions use."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    if not (pred.is_cuda and gt.is_cuda) or pred.dtype != torch.uint8 or gt.dtype != torch.uint8:
+        raise ValueError("psnr_ssim_device needs torch.uint8 CUDA tensors")
+    if pred.shape != gt.shape or pred.dim() != 4:
+        raise ValueError(f"shape mismatch or not [N,H,W,C]: {tuple(pred.shape)} vs {tuple(gt.shape)}")
+    lib = _lib.load()
+    pred, gt = pred.contiguous(), gt.contiguous()
+    N, H, W, Cc = pred.shape
+    chunks = lib.rg_metrics_ssim_chunks(H, W)
+    if chunks < 1:
+        raise ValueError(f"SSIM on the GPU needs 7 <= H, 7 <= W <= 8198 (got {H}x{W})")
+    dev = pred.device
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    sse = torch.empty((N,), dtype=torch.int64, device=dev)
+    smap = torch.empty((N, Cc, H - 6, W - 6), dtype=torch.float64, device=dev)
+    csum = torch.empty((N, Cc, chunks), dtype=torch.float64, device=dev)
+    NP = 7 ** 2
+    cov_norm = NP / (NP - 1)
+    C1, C2 = (K1 * data_range) ** 2, (K2 * data_range) ** 2
+    _lib.check(lib.rg_metrics_sse_u8(pred.data_ptr(), gt.data_ptr(), N, H * W * Cc, sse.data_ptr(), stream), "rg_metrics_sse_u8")
+    _lib.check(lib.rg_metrics_ssim_u8(pred.data_ptr(), gt.data_ptr(), N, H, W, Cc, C1, C2, cov_norm, smap.data_ptr(),
+                                      csum.data_ptr(), stream), "rg_metrics_ssim_u8")
+    sse_h = sse.cpu().numpy()
+    csum_h = csum.cpu().numpy()
+    count = (H - 6) * (W - 6)
+    psnrs, ssims = [], []
+    for n in range(N):
+        err = np.float64(int(sse_h[n])) / (H * W * Cc)              # == np.mean of the exact integer squares
+        with np.errstate(divide="ignore"):
+            psnrs.append(float(10 * np.log10((data_range ** 2) / err)))
+        vals = np.empty(Cc, dtype=np.float64)
+        for c in range(Cc):
+            t = 0.0
+            for v in csum_h[n, c]:
+                t += float(v)                                        # numpy adds its buffer chunks in order
+            vals[c] = np.float64(t) / count
+        ssims.append(float(vals.mean()))
+    return psnrs, ssims
 
 
 class MetricsCalculator:

@@ -237,6 +237,26 @@ int rg_scale_f32(const float* x, float a, int64_t n, float* y, rg_stream_t strea
 int rg_cast_f32_bf16(const float* x, int64_t n, void* y, rg_stream_t stream);
 int rg_memset_zero(void* p, int64_t bytes, rg_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K15  per-image PSNR / SSIM on u8 images in HBM (SURVEY 8f "f2"), bit-exact against the reference's
+ *      float64 CPU bookkeeping.  Replaces MetricsCalculator.calculate_psnr / calculate_ssim
+ *      (/root/reference/src/metrics.py:82-96 -> skimage.metrics.peak_signal_noise_ratio /
+ *      structural_similarity with data_range=255, channel_axis=2).
+ *   pred, gt: u8 [N][H][W][C] (channels last, contiguous).
+ *   rg_metrics_sse_u8: sse[n] = sum over the image of (pred-gt)^2, exact (uint64).  PSNR = 10 log10(255^2 /
+ *     (sse / elems)) is finished by the caller in float64.
+ *   rg_metrics_ssim_u8: writes the cropped SSIM map (float64 [N][C][H-6][W-6]) into smap_ws and, per (n, c),
+ *     rg_metrics_ssim_chunks(H, W) partial sums into chunk_sums [N][C][chunks]; the caller adds them left to right
+ *     starting from 0.0 and divides by (H-6)*(W-6) to obtain exactly the value numpy's mean of the cropped view
+ *     gives.  c1 = (K1*255)^2, c2 = (K2*255)^2, cov_norm = 49/48 are passed in so that they are the caller's own
+ *     float64 values.  7x7 uniform window, "reflect" borders; needs H, W >= 7 and W - 6 <= 8192.
+ * ------------------------------------------------------------------------------------------- */
+int rg_metrics_sse_u8(const uint8_t* pred, const uint8_t* gt, int32_t N, int64_t elems_per_image, uint64_t* sse,
+                      rg_stream_t stream);
+int rg_metrics_ssim_chunks(int32_t H, int32_t W);   /* number of partial sums per (image, channel); -1 if unsupported */
+int rg_metrics_ssim_u8(const uint8_t* pred, const uint8_t* gt, int32_t N, int32_t H, int32_t W, int32_t C, double c1,
+                       double c2, double cov_norm, double* smap_ws, double* chunk_sums, rg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -346,7 +346,49 @@ def case_layout_and_io(seed=90):
     return max(e1, e2, float(e3), e4 * 1e-0 if e4 > 1e-6 else 0.0), 1e-6
 
 
+def case_metrics(N=2, H=64, W=96, C=3, kind="noisy", seed=100):
+    """GPU PSNR / SSIM (csrc/metrics.cu) must equal the float64 numpy/scipy restatement of the scikit-image calls
+    BIT FOR BIT (metric bookkeeping is exact).  Returns the number of values that differ."""
+    import numpy as np
+    from image_restoration_and_enhancement_b200 import metrics
+    rng = np.random.default_rng(seed)
+    if kind == "random":
+        gt = rng.integers(0, 256, (N, H, W, C), dtype=np.uint8)
+        pred = rng.integers(0, 256, (N, H, W, C), dtype=np.uint8)
+    else:
+        yy, xx = np.mgrid[0:H, 0:W]
+        base = np.stack([127 + 100 * np.sin(xx / (5.0 + c) + n) * np.cos(yy / (7.0 + n)) for n in range(N)
+                         for c in range(C)]).reshape(N, C, H, W).transpose(0, 2, 3, 1)
+        gt = np.clip(base, 0, 255).astype(np.uint8)
+        if kind == "identical":
+            pred = gt.copy()
+        elif kind == "constant":
+            gt = np.full((N, H, W, C), 37, np.uint8)
+            pred = np.full((N, H, W, C), 200, np.uint8)
+        else:
+            pred = np.clip(gt.astype(np.float64) + rng.normal(0, 6.5, gt.shape), 0, 255).astype(np.uint8)
+    calc = metrics.MetricsCalculator(use_lpips=False)
+    want_p = [calc.calculate_psnr(pred[n], gt[n]) for n in range(N)]
+    want_s = [calc.calculate_ssim(pred[n], gt[n]) for n in range(N)]
+    got_p, got_s = metrics.psnr_ssim_device(torch.from_numpy(pred).to(DEV), torch.from_numpy(gt).to(DEV))
+    bad = sum(np.float64(a).tobytes() != np.float64(b).tobytes() for a, b in zip(want_p + want_s, got_p + got_s))
+    if bad:
+        print("metrics mismatch", kind, (N, H, W, C), list(zip(want_p, got_p)), list(zip(want_s, got_s)))
+    return float(bad), 0.0
+
+
 CASES = {
+    # ---- PSNR / SSIM on the GPU: bit equality with the float64 CPU bookkeeping
+    "metrics_512_noisy": lambda: case_metrics(N=2, H=512, W=512, kind="noisy", seed=100),
+    "metrics_512_random": lambda: case_metrics(N=1, H=512, W=512, kind="random", seed=101),
+    "metrics_identical": lambda: case_metrics(N=1, H=64, W=64, kind="identical", seed=102),
+    "metrics_constant": lambda: case_metrics(N=1, H=40, W=40, kind="constant", seed=103),
+    "metrics_ragged": lambda: case_metrics(N=3, H=37, W=50, kind="noisy", seed=104),
+    "metrics_min_7x7": lambda: case_metrics(N=2, H=7, W=7, kind="random", seed=105),
+    "metrics_wide_multi_chunk": lambda: case_metrics(N=1, H=24, W=2000, kind="noisy", seed=106),
+    "metrics_tall_gray": lambda: case_metrics(N=2, H=700, W=300, C=1, kind="noisy", seed=107),
+    "metrics_8x13": lambda: case_metrics(N=1, H=8, W=13, kind="random", seed=108),
+
     # --- tcgen05 GEMM, plain linear layers
     "linear_basic": lambda: case_linear(),
     "linear_ragged_n320": lambda: case_linear(M=300, K=320, N=320, seed=1),
