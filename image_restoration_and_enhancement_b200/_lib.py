@@ -37,7 +37,7 @@ class RgAttn(C.Structure):
                 ("k_stride_b", C.c_int64), ("k_stride_t", C.c_int64), ("k_stride_h", C.c_int64),
                 ("v_stride_b", C.c_int64), ("v_stride_t", C.c_int64), ("v_stride_h", C.c_int64),
                 ("o_stride_b", C.c_int64), ("o_stride_t", C.c_int64), ("o_stride_h", C.c_int64),
-                ("scale", C.c_float), ("dtype", C.c_int32)]
+                ("scale", C.c_float), ("dtype", C.c_int32), ("causal", C.c_int32)]
 
 
 class RgGn(C.Structure):
@@ -82,6 +82,9 @@ SIGNATURES = {
     "rg_scale_f32": (C.c_int, [_p, _f32, _i64, _p, _p]),
     "rg_cast_f32_bf16": (C.c_int, [_p, _i64, _p, _p]),
     "rg_memset_zero": (C.c_int, [_p, _i64, _p]),
+    "rg_embed_tokens": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _p, _p]),
+    "rg_quick_gelu_bf16": (C.c_int, [_p, _i64, _p]),
+    "rg_cast_bf16_f32": (C.c_int, [_p, _i64, _p, _p]),
     "rg_metrics_sse_u8": (C.c_int, [_p, _p, _i32, _i64, _p, _p]),
     "rg_metrics_ssim_chunks": (C.c_int, [_i32, _i32]),
     "rg_metrics_ssim_u8": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, C.c_double, C.c_double, C.c_double, _p, _p, _p]),

@@ -87,7 +87,7 @@ constexpr float kLazyRescale = 8.0f;       // raise the running max only when a 
 
 // All barrier phases are indexed by the CTA-global key-tile counter G = (items done) * n_kv + j, which is also the
 // K/V ring position; score buffer G % SBUF is used for the (G / SBUF)-th time.
-template <int DKA, int DQK, int DV, int BKV, int SBUF, bool PSEP, int STAGES, bool F16>
+template <int DKA, int DQK, int DV, int BKV, int SBUF, bool PSEP, int STAGES, bool F16, bool CAUSAL = false>
 __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
     using Cfg = AttnCfg<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16>;
     extern __shared__ __align__(16) uint8_t smem[];                    // window-relative base 0: no static smem
@@ -296,6 +296,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                     for (int i = 0; i < BKV; ++i)
                         if (i >= kv_left) s[i] = -INFINITY;
                 }
+                if constexpr (CAUSAL) {                          // key index <= query index (CLIP text encoder)
+                    const int lim = qp * 256 + t * 128 + row - j * BKV;
+#pragma unroll
+                    for (int i = 0; i < BKV; ++i)
+                        if (i > lim) s[i] = -INFINITY;
+                }
                 float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
 #pragma unroll
                 for (int i = 4; i < BKV; i += 8) {
@@ -427,12 +433,12 @@ static int encode_qkv_map(CUtensorMap* m, const void* base, int d, int heads, lo
                              CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int DKA, int DQK, int DV, int BKV, int SBUF, bool PSEP, int STAGES, bool F16>
+template <int DKA, int DQK, int DV, int BKV, int SBUF, bool PSEP, int STAGES, bool F16, bool CAUSAL = false>
 static int launch_attn(const rg_attn_t* a, cudaStream_t stream) {
     using Cfg = AttnCfg<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(attention_kernel<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16>,
+        cudaError_t e = cudaFuncSetAttribute(attention_kernel<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16, CAUSAL>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attention_kernel)");
         attr_done = true;
@@ -454,7 +460,7 @@ static int launch_attn(const rg_attn_t* a, cudaStream_t stream) {
     p.scale_log2 = a->scale * 1.4426950408889634f;
     p.trace = g_attn_trace;
     const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
-    attention_kernel<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16><<<grid, kAttnThreads, Cfg::SMEM_BYTES, stream>>>(p);
+    attention_kernel<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16, CAUSAL><<<grid, kAttnThreads, Cfg::SMEM_BYTES, stream>>>(p);
     count_launch();
     return check_launch("attention_kernel");
 }
@@ -483,6 +489,7 @@ extern "C" int rg_attention(const rg_attn_t* a, rg_stream_t stream_) {
     const int dv = (a->d + 15) / 16 * 16;
     // template arguments: DKA (64-wide atoms of d), DQK (k extent of Q K^T), DV (n extent of P V), BKV, SBUF, PSEP, STAGES, F16
     if (a->dtype == RG_DT_F16) {
+        if (a->causal) return set_error(RG_ERR_ARG, "attention: the causal path is bf16 only");
         // fp16 operands: DV includes the ones column at index d (inside the padding for d = 40, one more 16-column step else)
         if (a->d == 40) return launch_attn<1, 48, 48, 128, 1, true, 4, true>(a, stream);
         if (a->d == 80) return launch_attn<2, 80, 96, 128, 1, false, 2, true>(a, stream);
@@ -490,6 +497,12 @@ extern "C" int rg_attention(const rg_attn_t* a, rg_stream_t stream_) {
         return set_error(RG_ERR_ARG, "attention: the fp16 path supports head dims 40, 80 and 160");
     }
     if (a->dtype != RG_DT_BF16) return set_error(RG_ERR_ARG, "attention: dtype must be RG_DT_BF16 or RG_DT_F16");
+    if (a->causal) {
+        // the CLIP text encoder's attention (12 heads of 64, 77 tokens); query i attends keys 0..i
+        if (a->Nq != a->Nk) return set_error(RG_ERR_ARG, "attention: causal needs Nq == Nk");
+        if (dv <= 64) return launch_attn<1, 64, 64, 128, 1, true, 4, false, true>(a, stream);
+        return set_error(RG_ERR_ARG, "attention: the causal path supports head dims up to 64 (bf16)");
+    }
     if (dv <= 48) return launch_attn<1, 48, 48, 128, 1, true, 4, false>(a, stream);
     if (dv <= 64) return launch_attn<1, 64, 64, 128, 1, true, 4, false>(a, stream);
     if (dv <= 80) return launch_attn<2, 80, 80, 128, 1, false, 2, false>(a, stream);

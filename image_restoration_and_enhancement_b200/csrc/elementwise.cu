@@ -187,6 +187,31 @@ __global__ void cast_f32_bf16_kernel(const float* x, long long n, __nv_bfloat16*
 using namespace rg;
 #define RG_STREAM(s) reinterpret_cast<cudaStream_t>(s)
 
+namespace rg {
+// CLIPTextEmbeddings: out[b*T + t][:] = token_embedding[ids[b*T + t]][:] + position_embedding[t][:]  (fp32, 4 per thread)
+__global__ void embed_tokens_kernel(const int32_t* ids, const float4* tok, const float4* pos, int rows, int T, int C4,
+                                    int vocab, float4* out) {
+    RG_GRID_STRIDE(i, (long long)rows * C4) {
+        const int r = (int)(i / C4), c = (int)(i % C4);
+        int id = ids[r];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        const float4 a = tok[(long long)id * C4 + c], b = pos[(long long)(r % T) * C4 + c];
+        out[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* x, long long n, float* y) {
+    RG_GRID_STRIDE(i, n) y[i] = __bfloat162float(x[i]);
+}
+// quick_gelu(x) = x * sigmoid(1.702 x), bf16 in place (CLIP MLP activation)
+__global__ void quick_gelu_bf16_kernel(__nv_bfloat162* x, long long n2) {
+    RG_GRID_STRIDE(i, n2) {
+        const float2 v = __bfloat1622float2(x[i]);
+        x[i] = __floats2bfloat162_rn(v.x / (1.f + __expf(-1.702f * v.x)), v.y / (1.f + __expf(-1.702f * v.y)));
+    }
+}
+
+}  // namespace rg
+
 extern "C" int rg_sched_step(const rg_sched_t* s, rg_stream_t stream) {
     if (!s || !s->eps_uc || !s->sample) return set_error(RG_ERR_ARG, "sched_step: null pointer");
     const bool hist = s->w[0] != 0.f || s->w[1] != 0.f || s->w[2] != 0.f || s->w[3] != 0.f || s->store_slot >= 0;
@@ -321,4 +346,28 @@ extern "C" int rg_memset_zero(void* p, int64_t bytes, rg_stream_t stream) {
     cudaError_t e = cudaMemsetAsync(p, 0, (size_t)bytes, RG_STREAM(stream));
     if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync");
     return RG_OK;
+}
+
+extern "C" int rg_embed_tokens(const int32_t* ids, const float* token_embedding, const float* position_embedding,
+                               int32_t B, int32_t T, int32_t C, int32_t vocab, float* out, rg_stream_t stream) {
+    if (!ids || !token_embedding || !position_embedding || !out || B < 1 || T < 1 || C < 4 || C % 4 || vocab < 1)
+        return set_error(RG_ERR_ARG, "embed_tokens: bad argument");
+    embed_tokens_kernel<<<grid_for((long long)B * T * (C / 4), 256), 256, 0, RG_STREAM(stream)>>>(
+        ids, reinterpret_cast<const float4*>(token_embedding), reinterpret_cast<const float4*>(position_embedding), B * T, T,
+        C / 4, vocab, reinterpret_cast<float4*>(out));
+    count_launch();
+    return check_launch("embed_tokens_kernel");
+}
+extern "C" int rg_quick_gelu_bf16(void* x, int64_t n, rg_stream_t stream) {
+    if (!x || n < 0 || n % 2) return set_error(RG_ERR_ARG, "quick_gelu_bf16: bad argument");
+    if (n == 0) return RG_OK;
+    quick_gelu_bf16_kernel<<<grid_for(n / 2, 256), 256, 0, RG_STREAM(stream)>>>(reinterpret_cast<__nv_bfloat162*>(x), n / 2);
+    count_launch();
+    return check_launch("quick_gelu_bf16_kernel");
+}
+extern "C" int rg_cast_bf16_f32(const void* x, int64_t n, float* y, rg_stream_t stream) {
+    if (!x || !y) return set_error(RG_ERR_ARG, "cast_bf16_f32: null pointer");
+    cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, RG_STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, y);
+    count_launch();
+    return check_launch("cast_bf16_f32_kernel");
 }

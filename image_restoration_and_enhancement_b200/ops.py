@@ -153,8 +153,10 @@ def linear(x: torch.Tensor, w: torch.Tensor, **kw):
     return (None if ob is None else ob.view(M, -1)), (None if of is None else of.view(M, -1))
 
 
-def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, out: torch.Tensor | None = None):
-    """q [B,Nq,H,d], k/v [B,Nk,H,d] bf16 or fp16 views (d contiguous) -> out bf16 [B,Nq,H,d] contiguous."""
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, out: torch.Tensor | None = None,
+              causal: bool = False):
+    """q [B,Nq,H,d], k/v [B,Nk,H,d] bf16 or fp16 views (d contiguous) -> out bf16 [B,Nq,H,d] contiguous.
+    ``causal``: query i attends keys 0..i (the CLIP text encoder; bf16, d <= 64)."""
     lib = _lib.load()
     B, Nq, Hh, d = q.shape
     Nk = k.shape[1]
@@ -171,6 +173,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, o
     p.o_stride_b, p.o_stride_t, p.o_stride_h = out.stride(0), out.stride(1), out.stride(2)
     p.scale = scale
     p.dtype = RG_DT_F16 if q.dtype == f16 else RG_DT_BF16
+    p.causal = 1 if causal else 0
     e0 = _prof_begin()
     check(lib.rg_attention(C.byref(p), _stream()), "rg_attention")
     _prof_end(e0, 4.0 * B * Hh * Nq * Nk * d, "attention", f"B={B} H={Hh} Nq={Nq} Nk={Nk} d={d}")
@@ -221,6 +224,30 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     check(_lib.load().rg_layernorm(x.data_ptr(), _dt(x), x.shape[0], x.shape[1], gamma.data_ptr(), beta.data_ptr(),
                                    eps, y.data_ptr(), _stream()), "rg_layernorm")
     _prof_end(e0, float(x.numel()) * (x.element_size() + 2), "layernorm", f"rows={x.shape[0]} C={x.shape[1]}")
+    return y
+
+
+def embed_tokens(ids: torch.Tensor, tok: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+    """CLIPTextEmbeddings: ids int32 [B,T] -> fp32 [B*T, C] = tok[ids] + pos[t]."""
+    assert ids.dtype == torch.int32 and ids.is_contiguous() and tok.dtype == f32 and pos.dtype == f32
+    B, T = ids.shape
+    out = torch.empty((B * T, tok.shape[1]), dtype=f32, device=ids.device)
+    check(_lib.load().rg_embed_tokens(ids.data_ptr(), tok.data_ptr(), pos.data_ptr(), B, T, tok.shape[1], tok.shape[0],
+                                      out.data_ptr(), _stream()), "rg_embed_tokens")
+    return out
+
+
+def quick_gelu_(x: torch.Tensor) -> torch.Tensor:
+    """x * sigmoid(1.702 x), bf16, in place."""
+    assert x.dtype == bf16 and x.is_contiguous()
+    check(_lib.load().rg_quick_gelu_bf16(x.data_ptr(), x.numel(), _stream()), "rg_quick_gelu_bf16")
+    return x
+
+
+def cast_bf16_f32(x: torch.Tensor) -> torch.Tensor:
+    assert x.dtype == bf16 and x.is_contiguous()
+    y = torch.empty(x.shape, dtype=f32, device=x.device)
+    check(_lib.load().rg_cast_bf16_f32(x.data_ptr(), x.numel(), y.data_ptr(), _stream()), "rg_cast_bf16_f32")
     return y
 
 

@@ -28,27 +28,99 @@ def shard(n_items: int, rank: int, world: int) -> list[int]:
     return list(range(rank, n_items, world))
 
 
-def run_task(pipe: RestorationPipeline, task: str, n_images: int, rank: int = 0, world: int = 1,
-             size: int = 512, batch: int | None = None) -> tuple[list[int], dict[str, list[float]], float]:
+# sweep task name -> directory name of the reference's pairs/ and predictions/ trees
+TASK_DIR = {"denoise": "denoise", "sr": "sr_x4", "colorize": "colorize", "inpaint": "inpaint"}
+
+
+def _score(preds: list[np.ndarray], gts: list[np.ndarray], backend: str) -> tuple[list[float], list[float]]:
+    """Per-image PSNR / SSIM.  "gpu": csrc/metrics.cu on the uploaded u8 batch; "cpu": the numpy/scipy bookkeeping.
+    Both give the same float64 bits (tests/test_kernels_gpu.py::metrics_*)."""
+    preds = [metrics._match_shape(p, g) for p, g in zip(preds, gts)]
+    if backend == "gpu":
+        psnrs, ssims = [None] * len(preds), [None] * len(preds)
+        by_shape: dict[tuple, list[int]] = {}
+        for i, g in enumerate(gts):
+            by_shape.setdefault(g.shape, []).append(i)
+        for idx in by_shape.values():
+            p, s = metrics.psnr_ssim_device(torch.from_numpy(np.stack([preds[i] for i in idx])).cuda(),
+                                            torch.from_numpy(np.stack([gts[i] for i in idx])).cuda())
+            for j, i in enumerate(idx):
+                psnrs[i], ssims[i] = p[j], s[j]
+        return psnrs, ssims
+    if backend != "cpu":
+        raise ValueError(f"unknown metrics backend {backend}")
     calc = metrics.MetricsCalculator(use_lpips=False)
+    return ([calc.calculate_psnr(p, g) for p, g in zip(preds, gts)], [calc.calculate_ssim(p, g) for p, g in zip(preds, gts)])
+
+
+def run_task(pipe, task: str, n_images: int, rank: int = 0, world: int = 1, size: int = 512, batch: int | None = None,
+             handoff_mode: str = "memory", metrics_backend: str = "gpu", workdir=None
+             ) -> tuple[list[int], dict[str, list[float]], float]:
+    """Predict + score this rank's share of one task.
+
+    ``handoff_mode`` selects what sits between the pipeline and the metrics (see handoff.py):
+      "disk"   the reference's two-script flow: the synthetic pairs are written under ``workdir/pairs`` with
+               cv2.imwrite, inputs are re-read with PIL, predictions saved by name under ``workdir/predictions`` and
+               re-read, like the ground truth, with cv2.imread;
+      "memory" the same encoders / decoders on byte buffers (identical arrays, no file system);
+      "none"   raw arrays straight through (no codec; NOT what the reference's evaluator scores for .jpg tasks).
+    """
+    from pathlib import Path
+    from . import handoff
     mine = shard(n_images, rank, world)
     bsz = batch or BATCH[task]
+    tdir = TASK_DIR[task]
     vals: dict[str, list[float]] = {"psnr": [], "ssim": []}
+    if handoff_mode == "disk":
+        if workdir is None:
+            raise ValueError('handoff_mode="disk" needs workdir')
+        pair_root, pred_dir = Path(workdir) / "pairs", Path(workdir) / "predictions" / tdir / "test"
+        pred_dir.mkdir(parents=True, exist_ok=True)
     t0 = time.time()
     for s in range(0, len(mine), bsz):
         idx = mine[s:s + bsz]
-        data = synth.batch(task, idx, size, size)
-        ims = [Image.fromarray(a) for a in data["input"]]
-        masks = [Image.fromarray(m) for m in data["mask"]] if "mask" in data else None
+        items = [synth.make_pair(task, i, size, size) for i in idx]
+        names = [handoff.input_name(tdir, i) for i in idx]
+        masks = None
+        if handoff_mode == "none":
+            ims = [Image.fromarray(it["input"]) for it in items]
+            gts = [it["gt"] for it in items]
+            if "mask" in items[0]:
+                masks = [Image.fromarray(it["mask"]) for it in items]
+        elif handoff_mode == "memory":
+            gray = tdir == "colorize"
+            ims = [handoff.roundtrip_dataset_image(it["input"][:, :, 0] if gray else it["input"], nm, "pil")
+                   for it, nm in zip(items, names)]
+            gts = [handoff.roundtrip_dataset_image(it["gt"], handoff.gt_name(tdir, i), "cv2") for it, i in zip(items, idx)]
+            if "mask" in items[0]:
+                masks = [handoff.roundtrip_dataset_image(it["mask"], nm, "pil_l") for it, nm in zip(items, names)]
+        elif handoff_mode == "disk":
+            for it, i in zip(items, idx):
+                handoff.write_pairs(pair_root, tdir, i, it)
+            base = pair_root / tdir / "test"
+            ims = [Image.open(base / "input" / nm).convert("RGB") for nm in names]       # generate_predictions.py:68
+            gts = [handoff.load_image(base / "gt" / handoff.gt_name(tdir, i)) for i in idx]
+            if "mask" in items[0]:
+                masks = [Image.open(base / "mask" / nm).convert("L") for nm in names]    # generate_predictions.py:74
+        else:
+            raise ValueError(f"unknown handoff_mode {handoff_mode}")
         outs = pipe.process_batch(ims, task, masks=masks)
-        for o, gt in zip(outs, data["gt"]):
-            m = calc.calculate_all(np.array(o.convert("RGB")), gt)
-            vals["psnr"].append(m["psnr"])
-            vals["ssim"].append(m["ssim"])
+        if handoff_mode == "none":
+            preds = [np.array(o.convert("RGB")) for o in outs]
+        elif handoff_mode == "memory":
+            preds = [handoff.roundtrip_prediction(o, nm) for o, nm in zip(outs, names)]
+        else:
+            for o, nm in zip(outs, names):
+                handoff.save_prediction(o, pred_dir / nm)                                # generate_predictions.py:83-84
+            preds = [handoff.load_image(pred_dir / nm) for nm in names]
+        p, q = _score(preds, gts, metrics_backend)
+        vals["psnr"] += p
+        vals["ssim"] += q
     return mine, vals, time.time() - t0
 
 
-def run_sweep(n_images: int = 100, tasks=TASKS, size: int = 512, seed: int = 42, random_init: int = 0) -> dict | None:
+def run_sweep(n_images: int = 100, tasks=TASKS, size: int = 512, seed: int = 42, random_init: int = 0,
+              handoff_mode: str = "memory", metrics_backend: str = "gpu", workdir=None) -> dict | None:
     """Call from every rank (torchrun).  Returns the evaluation dict on rank 0, None elsewhere."""
     import torch.distributed as dist
     rank = dist.get_rank() if dist.is_initialized() else 0
@@ -58,7 +130,8 @@ def run_sweep(n_images: int = 100, tasks=TASKS, size: int = 512, seed: int = 42,
     pipe = RestorationPipeline(device="cuda", config=cfg, seed=seed, strict=True)
     results = {}
     for task in tasks:
-        idx, vals, secs = run_task(pipe, task, n_images, rank, world, size)
+        idx, vals, secs = run_task(pipe, task, n_images, rank, world, size, handoff_mode=handoff_mode,
+                                   metrics_backend=metrics_backend, workdir=workdir)
         full = metrics.gather_per_image(idx, vals)
         if rank == 0:
             results[task] = metrics.summarize(task, full, n_images)
@@ -72,7 +145,8 @@ if __name__ == "__main__":
     if "RANK" in os.environ:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
         dist.init_process_group("nccl")
-    res = run_sweep(n_images=int(os.environ.get("SWEEP_IMAGES", "16")))
+    res = run_sweep(n_images=int(os.environ.get("SWEEP_IMAGES", "16")), handoff_mode=os.environ.get("SWEEP_HANDOFF", "memory"),
+                    metrics_backend=os.environ.get("SWEEP_METRICS", "gpu"), workdir=os.environ.get("SWEEP_WORKDIR"))
     if res is not None:
         print(json.dumps(res, default=float))
     if dist.is_initialized():

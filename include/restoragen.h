@@ -97,7 +97,7 @@ typedef struct rg_conv {
 int rg_conv2d(const rg_conv_t* p, rg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
- * K5/K6  fused flash-style attention on tcgen05: O = softmax(scale * Q K^T) V, no mask.
+ * K5/K6  fused flash-style attention on tcgen05: O = softmax(scale * Q K^T) V, no mask or a causal mask.
  *   replaces F.scaled_dot_product_attention in attn1 (self, N = H*W tokens) and attn2
  *   (cross, 77 CLIP tokens) of every BasicTransformerBlock.
  *   q/k/v are bf16 or fp16, out is bf16: [B][tokens][heads][d] views with arbitrary (multiple-of-8) strides.
@@ -115,6 +115,7 @@ typedef struct rg_attn {
     int64_t o_stride_b, o_stride_t, o_stride_h;
     float scale;
     int32_t dtype;                 /* element type of q, k, v: RG_DT_BF16 (default) or RG_DT_F16; out is always bf16 */
+    int32_t causal;                /* 1: query i attends keys 0..i only (CLIPTextModel's causal mask); bf16, d <= 64, Nq == Nk */
 } rg_attn_t;
 
 int rg_attention(const rg_attn_t* p, rg_stream_t stream);
@@ -236,6 +237,18 @@ int rg_mask_nearest(const float* mask, int32_t N, int32_t H, int32_t W, int32_t 
 int rg_scale_f32(const float* x, float a, int64_t n, float* y, rg_stream_t stream);
 int rg_cast_f32_bf16(const float* x, int64_t n, void* y, rg_stream_t stream);
 int rg_memset_zero(void* p, int64_t bytes, rg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K16  CLIP text encoder glue (SURVEY 8f "f3"; transformers CLIPTextModel behind pipe.text_encoder,
+ *      /root/reference/outputs/models/denoising/best/text_encoder/config.json): the 12 layers run on rg_layernorm,
+ *      rg_conv2d (as linear) and rg_attention with causal = 1; these two cover what is left.
+ *   rg_embed_tokens: out f32 [B*T][C] = token_embedding[ids[b][t]] + position_embedding[t]  (CLIPTextEmbeddings)
+ *   rg_quick_gelu_bf16: x <- x * sigmoid(1.702 x) in place on n bf16 values (hidden_act "quick_gelu")
+ * ------------------------------------------------------------------------------------------- */
+int rg_embed_tokens(const int32_t* ids, const float* token_embedding, const float* position_embedding, int32_t B,
+                    int32_t T, int32_t C, int32_t vocab, float* out, rg_stream_t stream);
+int rg_quick_gelu_bf16(void* x, int64_t n, rg_stream_t stream);
+int rg_cast_bf16_f32(const void* x, int64_t n, float* y, rg_stream_t stream);   /* last_hidden_state handed out as fp32 */
 
 /* ---------------------------------------------------------------------------------------------
  * K15  per-image PSNR / SSIM on u8 images in HBM (SURVEY 8f "f2"), bit-exact against the reference's

@@ -149,7 +149,7 @@ def case_conv_strided_out(seed=29):
 
 
 # ------------------------------------------------------------------------------------------------ attention
-def case_attention(B=2, heads=8, d=40, Nq=1024, Nk=None, seed=20, fused_qkv=True, dtype=torch.bfloat16):
+def case_attention(B=2, heads=8, d=40, Nq=1024, Nk=None, seed=20, fused_qkv=True, dtype=torch.bfloat16, causal=False):
     """``dtype`` fp16: the UNet's path (two exponentials per MUFU op, denominator from a ones column of V)."""
     _setup()
     Nk = Nq if Nk is None else Nk
@@ -166,10 +166,28 @@ def case_attention(B=2, heads=8, d=40, Nq=1024, Nk=None, seed=20, fused_qkv=True
         v = kv[:, :, C:].unflatten(2, (heads, d))
     scale = d ** -0.5
     ref = F.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2),
-                                         v.float().transpose(1, 2)).transpose(1, 2)
-    out = ops.attention(q, k, v, scale)
+                                         v.float().transpose(1, 2), is_causal=causal).transpose(1, 2)
+    out = ops.attention(q, k, v, scale, causal=causal)
     torch.cuda.synchronize()
     return rel_l2(out, ref), TOL_ATTN
+
+
+def case_clip_glue(seed=49):
+    """CLIPTextEmbeddings gather + add, quick_gelu in place, bf16 -> fp32 cast."""
+    _setup()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    tok = torch.randn((1000, 768), generator=g).to(DEV)
+    pos = torch.randn((77, 768), generator=g).to(DEV)
+    ids = torch.randint(0, 1000, (3, 77), generator=g).to(torch.int32).to(DEV)
+    e = ops.embed_tokens(ids, tok, pos)
+    ref = (tok[ids.long()] + pos[None]).view(-1, 768)
+    x = _rand((231, 3072), seed + 1, 2.0)
+    want = (x.float() * torch.sigmoid(1.702 * x.float()))
+    got = ops.quick_gelu_(x.clone())
+    c = ops.cast_bf16_f32(x)
+    torch.cuda.synchronize()
+    assert torch.equal(e, ref) and torch.equal(c, x.float())
+    return rel_l2(got, want), TOL_BF16
 
 
 def case_attention_large_logits(seed=47):
@@ -378,6 +396,12 @@ def case_metrics(N=2, H=64, W=96, C=3, kind="noisy", seed=100):
 
 
 CASES = {
+    # ---- CLIP text encoder pieces (causal attention on the tcgen05 kernel, embedding gather, quick_gelu)
+    "attn_causal_clip_77": lambda: case_attention(B=2, heads=12, d=64, Nq=77, seed=120, causal=True),
+    "attn_causal_multi_tile": lambda: case_attention(B=1, heads=3, d=64, Nq=300, seed=121, causal=True),
+    "attn_causal_d40": lambda: case_attention(B=1, heads=2, d=40, Nq=130, seed=122, causal=True),
+    "clip_glue": lambda: case_clip_glue(),
+
     # ---- PSNR / SSIM on the GPU: bit equality with the float64 CPU bookkeeping
     "metrics_512_noisy": lambda: case_metrics(N=2, H=512, W=512, kind="noisy", seed=100),
     "metrics_512_random": lambda: case_metrics(N=1, H=512, W=512, kind="random", seed=101),

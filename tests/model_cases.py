@@ -208,6 +208,29 @@ def case_pipeline(task="denoise", H=512, W=512, B=1, seed=0, graph=True):
 
 # ------------------------------------------------------------------------------------------------ timing helper
 @torch.no_grad()
+def case_clip_text(seed=7):
+    """CLIP text encoder on librestoragen (text_encoder.py) against transformers' CLIPTextModel in fp32 on the same
+    weights and ids: the reference's default prompts and the empty negative prompt.  Returns (rel-L2, tolerance)."""
+    _setup()
+    import json
+    from pathlib import Path
+    import image_restoration_and_enhancement_b200 as pkg
+    from image_restoration_and_enhancement_b200.pipelines import make_text_encoder
+    from image_restoration_and_enhancement_b200.text_encoder import CLIPTextB200
+    ref_model = make_text_encoder(seed).to(DEV)
+    table = json.loads((Path(pkg.__file__).parent / "data" / "default_prompt_ids.json").read_text())
+    ids = torch.tensor(list(table.values()), dtype=torch.long, device=DEV)
+    with torch.no_grad():
+        want = ref_model(ids)[0].float()
+    mine = CLIPTextB200(ref_model.state_dict(), device=DEV)
+    got = mine(ids)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape == (ids.shape[0], 77, 768) and got.dtype == torch.float32
+    one = mine(ids[:1])                                   # batch-invariant: a prompt alone gives the same embedding
+    assert torch.equal(one, got[:1])
+    return rel_l2(got, want), UNET_TOL
+
+
 def time_unet(B=8, cfg=True, h=64, w=64, iters=5, graph=True, in_channels=4):
     _setup()
     sd = random_state_dict(unet_param_shapes(in_channels=in_channels), 0)

@@ -1,0 +1,86 @@
+"""The predict -> evaluate hand-off (SURVEY 8f "f1"): the in-memory codec round trip yields exactly the arrays the
+reference's two-script, file-based flow scores (scripts/generate_predictions.py:83-84 PIL save by input name ->
+src/metrics.py:40-46 cv2.imread), and the sharded sweep gives identical metrics either way."""
+import numpy as np
+import pytest
+from PIL import Image
+
+from image_restoration_and_enhancement_b200 import handoff, metrics, sweep, synth
+
+
+def _img(i=0, size=96):
+    return synth.make_pair("denoise", i, size, size)
+
+
+@pytest.mark.parametrize("name", ["000001.jpg", "000001.jpeg", "000001.png"])
+def test_prediction_roundtrip_memory_equals_disk(tmp_path, name):
+    pred = Image.fromarray(_img(1)["input"])
+    handoff.save_prediction(pred, tmp_path / name)
+    on_disk = handoff.load_image(tmp_path / name)
+    in_mem = handoff.roundtrip_prediction(pred, name)
+    assert on_disk.dtype == np.uint8 and np.array_equal(on_disk, in_mem)
+    assert (tmp_path / name).read_bytes() == handoff.encode_prediction(pred, name)
+
+
+def test_png_handoff_is_identity_and_jpeg_is_not():
+    arr = _img(2)["input"]
+    assert np.array_equal(handoff.roundtrip_prediction(Image.fromarray(arr), "x.png"), arr)
+    assert np.array_equal(handoff.decode_cv2(handoff.encode_prediction(Image.fromarray(arr), "x.png")), arr)
+    jpg = handoff.roundtrip_prediction(Image.fromarray(arr), "x.jpg")
+    assert jpg.shape == arr.shape and not np.array_equal(jpg, arr)
+    gt = _img(2)["gt"]
+    # the codec moves the metric: scoring the raw array is not what the reference's evaluator does for .jpg tasks
+    assert metrics.psnr(gt, jpg) != metrics.psnr(gt, arr)
+
+
+@pytest.mark.parametrize("task", ["denoise", "sr", "colorize", "inpaint"])
+def test_dataset_roundtrip_memory_equals_disk(tmp_path, task):
+    tdir = sweep.TASK_DIR[task]
+    pair = synth.make_pair(task, 3, 64, 64)
+    handoff.write_pairs(tmp_path, tdir, 3, pair)
+    base = tmp_path / tdir / "test"
+    nm = handoff.input_name(tdir, 3)
+    assert nm.endswith(".png") == (task == "colorize")
+    disk_in = np.array(Image.open(base / "input" / nm).convert("RGB"))
+    src = pair["input"][:, :, 0] if task == "colorize" else pair["input"]
+    assert np.array_equal(disk_in, np.array(handoff.roundtrip_dataset_image(src, nm, "pil")))
+    if task == "colorize":                                  # PNG: the predictor sees the gray image exactly
+        assert np.array_equal(disk_in, pair["input"])
+    disk_gt = handoff.load_image(base / "gt" / handoff.gt_name(tdir, 3))
+    assert np.array_equal(disk_gt, handoff.roundtrip_dataset_image(pair["gt"], handoff.gt_name(tdir, 3), "cv2"))
+    if task == "inpaint":
+        disk_mask = np.array(Image.open(base / "mask" / nm).convert("L"))
+        assert np.array_equal(disk_mask, np.array(handoff.roundtrip_dataset_image(pair["mask"], nm, "pil_l")))
+
+
+def test_unsupported_extension_is_an_error():
+    with pytest.raises(ValueError):
+        handoff.roundtrip_prediction(Image.fromarray(_img(0)["input"]), "x.bmp")
+    with pytest.raises(ValueError):
+        handoff.decode_cv2(b"not an image")
+
+
+class _BlurPipe:
+    """Stand-in for RestorationPipeline on CPU: a deterministic "restoration" (3x3 box blur)."""
+
+    def process_batch(self, images, task, masks=None, **kw):
+        import cv2
+        if task == "inpaint":
+            assert masks is not None and all(m.mode == "L" for m in masks)
+        return [Image.fromarray(cv2.blur(np.array(im.convert("RGB")), (3, 3))) for im in images]
+
+
+@pytest.mark.parametrize("task", ["denoise", "colorize", "inpaint"])
+def test_sweep_disk_flow_equals_memory_flow(tmp_path, task):
+    pipe = _BlurPipe()
+    idx_d, disk, _ = sweep.run_task(pipe, task, 5, size=64, batch=2, handoff_mode="disk", metrics_backend="cpu", workdir=tmp_path)
+    idx_m, mem, _ = sweep.run_task(pipe, task, 5, size=64, batch=2, handoff_mode="memory", metrics_backend="cpu")
+    assert idx_d == idx_m == [0, 1, 2, 3, 4]
+    assert disk == mem                                      # float64 equality, value by value
+    # ... and equals the reference's directory-based evaluation of the files just written
+    ev = metrics.evaluate_task(tmp_path / "predictions" / sweep.TASK_DIR[task] / "test",
+                               tmp_path / "pairs" / sweep.TASK_DIR[task] / "test" / "gt", task, use_lpips=False)
+    assert ev["num_samples"] == 5
+    assert ev["metrics"]["psnr"]["mean"] == np.mean(mem["psnr"]) and ev["metrics"]["ssim"]["median"] == np.median(mem["ssim"])
+    _, raw, _ = sweep.run_task(pipe, task, 5, size=64, batch=2, handoff_mode="none", metrics_backend="cpu")
+    assert raw != mem                                       # codecs on both sides change what is scored

@@ -22,6 +22,12 @@ def test_unet_step_parity(cin, B, cfg, t):
     assert err <= tol, f"UNet rel-L2 {err:.3e} > {tol}"
 
 
+def test_clip_text_encoder_parity():
+    """pipe.text_encoder on the sm_100a kernels vs transformers' CLIPTextModel (fp32), default prompts + empty prompt."""
+    err, tol = mc.case_clip_text()
+    assert err <= tol, f"CLIP last_hidden_state rel-L2 {err:.3e} > {tol}"
+
+
 def test_vae_encode_parity():
     err, tol = mc.case_vae_encode(1)
     assert err <= tol, f"VAE encoder moments rel-L2 {err:.3e}"
@@ -84,3 +90,35 @@ def test_restoration_pipeline_drop_in():
     assert (np.array(again) == np.array(res["final"])).all()              # seeded => bitwise reproducible
     outs = rp.process_batch([im, im], "denoise", denoise_strength=0.3)
     assert (np.array(outs[0]) == np.array(res["final"])).all() and (np.array(outs[1]) == np.array(res["final"])).all()
+
+
+def test_checkpoint_directory_roundtrip(tmp_path):
+    """SURVEY 8f "f4": a diffusers-layout model directory (what the reference's ``from_pretrained(model_path,
+    torch_dtype=..., use_safetensors=True)`` reads, src/inference.py:162-166) written by save_pretrained loads back to a
+    pipeline that produces the same image bit for bit, prompt -> CLIP -> UNet -> VAE included."""
+    from image_restoration_and_enhancement_b200.pipelines import (StableDiffusionImg2ImgPipeline,
+                                                                  StableDiffusionInpaintPipeline)
+    prompt = "clean high quality photo, no noise, sharp details"
+    img = mc.synth_image(5, 256, 256)[None]
+    kw = dict(prompt=prompt, image=img, strength=0.3, num_inference_steps=10, guidance_scale=5.0, output_type="np_u8")
+    a = StableDiffusionImg2ImgPipeline.from_random_init(seed=3)
+    a.save_pretrained(tmp_path / "best")
+    for sub in ("unet/config.json", "unet/diffusion_pytorch_model.safetensors", "vae/diffusion_pytorch_model.safetensors",
+                "scheduler/scheduler_config.json", "text_encoder/config.json", "model_index.json"):
+        assert (tmp_path / "best" / sub).exists(), sub
+    want = a.to("cuda")(generator=torch.Generator(device="cuda").manual_seed(42), **kw).images
+    with pytest.raises(RuntimeError):
+        a.save_pretrained(tmp_path / "late")                                # host weights are gone after .to()
+    del a
+    b = StableDiffusionImg2ImgPipeline.from_pretrained(str(tmp_path / "best"), torch_dtype=torch.float16, use_safetensors=True)
+    assert type(b.scheduler).__name__ == "PNDMScheduler"
+    b = b.to("cuda")
+    b.text_encoder.eval(); b.unet.eval(); b.vae.eval()                       # src/inference.py:178-180
+    assert next(b.text_encoder.parameters()).device.type == "cuda"
+    got = b(generator=torch.Generator(device="cuda").manual_seed(42), **kw).images
+    assert (got == want).all()
+    with pytest.raises(ValueError):                                          # a 4-channel UNet is not an inpainting model
+        StableDiffusionInpaintPipeline.from_pretrained(str(tmp_path / "best"))
+    (tmp_path / "best" / "vae" / "diffusion_pytorch_model.safetensors").unlink()
+    with pytest.raises(OSError):                                             # incomplete directory (src/inference.py:227)
+        StableDiffusionImg2ImgPipeline.from_pretrained(str(tmp_path / "best"))
