@@ -66,6 +66,7 @@ SIGNATURES = {
     "rg_softmax_rows": (C.c_int, [_p, _i64, _i32, _i64, _p]),
     "rg_groupnorm_stats": (C.c_int, [C.POINTER(RgGn), _p]),
     "rg_groupnorm_apply": (C.c_int, [C.POINTER(RgGn), _p]),
+    "rg_groupnorm": (C.c_int, [C.POINTER(RgGn), _p]),
     "rg_layernorm": (C.c_int, [_p, _i32, _i64, _i32, _p, _p, _f32, _p, _p]),
     "rg_timestep_embedding": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "rg_sched_step": (C.c_int, [C.POINTER(RgSched), _p]),

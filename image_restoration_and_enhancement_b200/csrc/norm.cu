@@ -3,6 +3,7 @@
 // Layout: x[n][pixel][C], C contiguous.  Every thread owns 8 consecutive channels (one 16-byte bf16 vector,
 // two float4 for fp32 input) for all pixels it visits, so the per-channel affine terms live in registers and
 // consecutive threads touch consecutive 16/32-byte pieces of a pixel row (fully coalesced).
+#include <type_traits>
 #include "common.cuh"
 #include "internal.h"
 
@@ -44,6 +45,44 @@ __device__ __forceinline__ void load8(const void* src, int Cs, int cs, const GnP
     }
 }
 
+// the same load split in two: raw 16/32-byte vectors first (so that an unrolled loop keeps only the packed words of
+// its U in-flight loads live), conversion to fp32 when they are consumed
+template <bool IN_F32> struct Raw8 { uint4 a; uint4 b; };
+template <> struct Raw8<false> { uint4 a; };
+template <bool IN_F32>
+__device__ __forceinline__ Raw8<IN_F32> load_raw8(const unsigned char* ptr, bool ok) {
+    Raw8<IN_F32> r;
+    r.a = make_uint4(0u, 0u, 0u, 0u);
+    if constexpr (IN_F32) {
+        r.b = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) {
+            const uint4* s = reinterpret_cast<const uint4*>(ptr);
+            r.a = s[0]; r.b = s[1];
+        }
+    } else {
+        if (ok) r.a = *reinterpret_cast<const uint4*>(ptr);
+    }
+    return r;
+}
+// byte address of the thread's 8 channels at pixel `pix` of image n, and the byte stride between its pixel visits
+template <bool IN_F32>
+__device__ __forceinline__ const unsigned char* pix_ptr(const void* src, int Cs, int cs, const GnParams& p, int n, long long pix) {
+    return reinterpret_cast<const unsigned char*>(src) + (((long long)n * p.HW + pix) * Cs + cs) * (IN_F32 ? 4 : 2);
+}
+template <bool IN_F32>
+__device__ __forceinline__ void unpack8(const Raw8<IN_F32>& r, float (&v)[8]) {
+    if constexpr (IN_F32) {
+        v[0] = __uint_as_float(r.a.x); v[1] = __uint_as_float(r.a.y); v[2] = __uint_as_float(r.a.z); v[3] = __uint_as_float(r.a.w);
+        v[4] = __uint_as_float(r.b.x); v[5] = __uint_as_float(r.b.y); v[6] = __uint_as_float(r.b.z); v[7] = __uint_as_float(r.b.w);
+    } else {
+        float2 f;
+        f = unpack_bf16x2(r.a.x); v[0] = f.x; v[1] = f.y;
+        f = unpack_bf16x2(r.a.y); v[2] = f.x; v[3] = f.y;
+        f = unpack_bf16x2(r.a.z); v[4] = f.x; v[5] = f.y;
+        f = unpack_bf16x2(r.a.w); v[6] = f.x; v[7] = f.y;
+    }
+}
+
 // workspace layout (floats): [RG_GN_MAX_IMAGES counters (int), zero between launches] [N][G][2] (mean, rstd) [N][blocks][G][2] partial (sum, sumsq)
 __device__ __forceinline__ float* gn_final(const GnParams& p) { return p.sums + RG_GN_MAX_IMAGES; }
 __device__ __forceinline__ float* gn_partials(const GnParams& p) { return gn_final(p) + (long long)p.N * p.groups * 2; }
@@ -69,55 +108,68 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const GnParams p) {
     const void* const src = first ? p.x1 : p.x2;
     const int Cs = first ? p.C1 : p.C2, cs = first ? c0 : c0 - p.C1;
     long long pix = p0 + tr;
-    for (; pix + 3LL * p.rpb < p1; pix += 4LL * p.rpb) {      // four independent loads in flight per thread
-        float v0[8], v1[8], v2[8], v3[8];
-        load8<IN_F32>(src, Cs, cs, p, n, pix, v0);
-        load8<IN_F32>(src, Cs, cs, p, n, pix + p.rpb, v1);
-        load8<IN_F32>(src, Cs, cs, p, n, pix + 2LL * p.rpb, v2);
-        load8<IN_F32>(src, Cs, cs, p, n, pix + 3LL * p.rpb, v3);
+    // U independent loads in flight per thread (8 x 16 B for bf16, 4 x 32 B for fp32); the accumulation below is in
+    // pixel order, exactly the order of the scalar tail loop, so the unroll factor does not change a single bit
+    constexpr int U = IN_F32 ? 4 : 8;
+    for (; pix < p1; pix += (long long)U * p.rpb) {
+        // ragged end: slots past the slice load nothing and contribute +0 (no serial tail loop -- its dependent
+        // load -> add chain cost one full memory latency per pixel)
+        Raw8<IN_F32> raw[U];
+        const unsigned char* ptr = pix_ptr<IN_F32>(src, Cs, cs, p, n, pix);
+        const long long step = (long long)p.rpb * Cs * (IN_F32 ? 4 : 2);
+        const int left = (int)((p1 - pix + p.rpb - 1) / p.rpb);   // visits of this thread that are still inside the slice
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {                          // same accumulation order as the scalar loop
-            s[i] += v0[i]; ss[i] += v0[i] * v0[i];
-            s[i] += v1[i]; ss[i] += v1[i] * v1[i];
-            s[i] += v2[i]; ss[i] += v2[i] * v2[i];
-            s[i] += v3[i]; ss[i] += v3[i] * v3[i];
+        for (int u = 0; u < U; ++u) {
+            raw[u] = load_raw8<IN_F32>(ptr, u < left);
+            ptr += step;
         }
-    }
-    for (; pix < p1; pix += p.rpb) {
-        float v[8];
-        load8<IN_F32>(src, Cs, cs, p, n, pix, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i] += v[i]; ss[i] += v[i] * v[i]; }
+        for (int u = 0; u < U; ++u) {                          // pixel order, channel by channel: the scalar order
+            float v[8];
+            unpack8<IN_F32>(raw[u], v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s[i] += v[i]; ss[i] += v[i] * v[i]; }
+        }
     }
     float* mine = s_red + ((long long)tr * p.tpr + tc) * 16;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { mine[i] = s[i]; mine[8 + i] = ss[i]; }
     __syncthreads();
+    // channel sums: output o = tc * 16 + k (k < 8: sum of channel tc*8+k, k >= 8: its sum of squares), rows added in
+    // slot order; all threads take part, consecutive threads read consecutive words
     float* chan = s_red + (long long)p.rpb * p.tpr * 16;      // [C][2]
-    if (tr == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float a = 0.f, b = 0.f;
-            for (int r = 0; r < p.rpb; ++r) {                 // fixed order over the row slots
-                const float* o = s_red + ((long long)r * p.tpr + tc) * 16;
-                a += o[i]; b += o[8 + i];
-            }
-            chan[(c0 + i) * 2] = a; chan[(c0 + i) * 2 + 1] = b;
-        }
+    const int row_words = p.tpr * 16;
+    for (int o = threadIdx.x; o < row_words; o += blockDim.x) {
+        float a = 0.f;
+        for (int r = 0; r < p.rpb; ++r) a += s_red[(long long)r * row_words + o];
+        const int k = o & 15;
+        chan[((o >> 4) * 8 + (k & 7)) * 2 + (k >> 3)] = a;
     }
     __syncthreads();
+    // group sums: four lanes per group, each adds a contiguous quarter of the group's channels in order, then
+    // ((q0 + q1) + (q2 + q3)) by two butterfly steps -- a fixed tree
     float* partials = gn_partials(p);
-    if ((int)threadIdx.x < p.groups) {
-        const int g = threadIdx.x;
+    {
+        const int g = threadIdx.x >> 2, q = threadIdx.x & 3;
+        const bool live = g < p.groups;                       // blockDim >= 4 * groups is checked on the host
         float a = 0.f, b = 0.f;
-        for (int c = g * p.cpg; c < (g + 1) * p.cpg; ++c) { a += chan[c * 2]; b += chan[c * 2 + 1]; }
-        float* dst = partials + (((long long)n * gridDim.x + blockIdx.x) * p.groups + g) * 2;
-        dst[0] = a; dst[1] = b;
+        if (live) {
+            const int lo = g * p.cpg + q * p.cpg / 4, hi = g * p.cpg + (q + 1) * p.cpg / 4;
+            for (int c = lo; c < hi; ++c) { a += chan[c * 2]; b += chan[c * 2 + 1]; }
+        }
+        if ((int)(threadIdx.x & ~31u) < p.groups * 4) {       // warp-uniform: whole warps run the shuffles
+            a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2);
+        }
+        if (live && q == 0) {
+            float* dst = partials + (((long long)n * gridDim.x + blockIdx.x) * p.groups + g) * 2;
+            dst[0] = a; dst[1] = b;
+        }
     }
-    // the block that finishes last for this image combines the partials in block order (fp64): the counter only
+    // the block that finishes last for this image combines the partials in a fixed order (fp64): the counter only
     // elects WHO does it, so the result does not depend on arrival order
     __shared__ int is_last;
-    __threadfence();
+    __threadfence();                                          // the partial writes above, before the arrival below
     __syncthreads();
     if (threadIdx.x == 0) {
         int* counter = reinterpret_cast<int*>(p.sums) + n;
@@ -126,18 +178,35 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const GnParams p) {
         if (is_last) *counter = 0;                            // self-resetting
     }
     __syncthreads();
-    if (is_last && (int)threadIdx.x < p.groups) {
+    // LPG lanes per group (8 if the block has 8 * groups threads in full warps, else 4 -- a function of C and groups
+    // only): lane q adds blocks [q*nb/LPG, (q+1)*nb/LPG) in block order -- independent L2 loads, eight in flight --
+    // then a butterfly over the LPG lanes: a fixed tree
+    const int lpg_shift = ((int)(blockDim.x & ~31u) >= p.groups * 8) ? 3 : 2;
+    if (is_last && (int)(threadIdx.x & ~31u) < (p.groups << lpg_shift)) {
         __threadfence();
-        const int g = threadIdx.x;
-        const volatile float* part = partials + ((long long)n * gridDim.x * p.groups + g) * 2;
+        const int lpg = 1 << lpg_shift;
+        const int g = threadIdx.x >> lpg_shift, q = threadIdx.x & (lpg - 1), nb = (int)gridDim.x;
         double sum = 0.0, sq = 0.0;
-        for (int b = 0; b < (int)gridDim.x; ++b) { sum += part[(long long)b * p.groups * 2]; sq += part[(long long)b * p.groups * 2 + 1]; }
-        const double inv_cnt = 1.0 / ((double)p.cpg * (double)p.HW);
-        const double m = sum * inv_cnt;
-        const double var = fmax(sq * inv_cnt - m * m, 0.0);
-        float* fin = gn_final(p) + ((long long)n * p.groups + g) * 2;
-        fin[0] = (float)m;
-        fin[1] = (float)(1.0 / sqrt(var + (double)p.eps));
+        if (g < p.groups) {
+            const float* part = partials + ((long long)n * nb * p.groups + g) * 2;
+            const int b1 = (q + 1) * nb / lpg;
+#pragma unroll 8
+            for (int b = q * nb / lpg; b < b1; ++b) {
+                const float2 v = __ldcg(reinterpret_cast<const float2*>(part + (long long)b * p.groups * 2));
+                sum += v.x; sq += v.y;
+            }
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1); sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2); sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+        if (lpg_shift == 3) { sum += __shfl_xor_sync(0xffffffffu, sum, 4); sq += __shfl_xor_sync(0xffffffffu, sq, 4); }
+        if (g < p.groups && q == 0) {
+            const double inv_cnt = 1.0 / ((double)p.cpg * (double)p.HW);
+            const double m = sum * inv_cnt;
+            const double var = fmax(sq * inv_cnt - m * m, 0.0);
+            float* fin = gn_final(p) + ((long long)n * p.groups + g) * 2;
+            fin[0] = (float)m;
+            fin[1] = (float)(1.0 / sqrt(var + (double)p.eps));
+        }
     }
 }
 
@@ -177,19 +246,124 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const GnParams p) {
     const void* const src = first ? p.x1 : p.x2;
     const int Cs = first ? p.C1 : p.C2, cs = first ? c0 : c0 - p.C1;
     long long pix = p0 + tr;
-    for (; pix + 3LL * p.rpb < p1; pix += 4LL * p.rpb) {      // four independent loads in flight per thread
-        float v0[8], v1[8], v2[8], v3[8];
-        load8<IN_F32>(src, Cs, cs, p, n, pix, v0);
-        load8<IN_F32>(src, Cs, cs, p, n, pix + p.rpb, v1);
-        load8<IN_F32>(src, Cs, cs, p, n, pix + 2LL * p.rpb, v2);
-        load8<IN_F32>(src, Cs, cs, p, n, pix + 3LL * p.rpb, v3);
-        emit(pix, v0); emit(pix + p.rpb, v1); emit(pix + 2LL * p.rpb, v2); emit(pix + 3LL * p.rpb, v3);
+    constexpr int U = IN_F32 ? 4 : 8;                          // independent loads in flight per thread
+    for (; pix < p1; pix += (long long)U * p.rpb) {
+        Raw8<IN_F32> raw[U];
+        const unsigned char* ptr = pix_ptr<IN_F32>(src, Cs, cs, p, n, pix);
+        const long long step = (long long)p.rpb * Cs * (IN_F32 ? 4 : 2);
+        const int left = (int)((p1 - pix + p.rpb - 1) / p.rpb);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            raw[u] = load_raw8<IN_F32>(ptr, u < left);
+            ptr += step;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long px = pix + (long long)u * p.rpb;
+            if (u < left) {
+                float v[8];
+                unpack8<IN_F32>(raw[u], v);
+                emit(px, v);
+            }
+        }
     }
-    for (; pix < p1; pix += p.rpb) {
-        float v[8];
-        load8<IN_F32>(src, Cs, cs, p, n, pix, v);
-        emit(pix, v);
+}
+
+// ---------------------------------------------------------------------------------------------- one-pass GroupNorm
+// Few-pixel levels (32x32 and below in the UNet): the slice of one (image, group) -- HW pixels x cpg channels -- fits in
+// shared memory, so one block reads it ONCE, reduces it in a fixed order, normalises it from shared memory and writes
+// the bf16 result: one launch and one HBM read instead of two launches and two reads.  No inter-block communication at
+// all, so the result is deterministic and independent of the batch size by construction.  An item is 4 consecutive
+// channels of one pixel (16 B fp32 / 8 B bf16); C1 is a multiple of 8, so an item never straddles the two sources.
+// grid = (groups, N), 256 threads, dynamic smem = HW * cpg * sizeof(input element)
+template <bool IN_F32>
+__global__ void __launch_bounds__(256) gn_fused_small_kernel(const GnParams p) {
+    extern __shared__ __align__(16) unsigned char s_slice[];
+    __shared__ double s_part[2][8];
+    __shared__ float s_stat[2];
+    __shared__ float s_scale[128], s_shift[128];
+    using Vec = typename std::conditional<IN_F32, float4, uint2>::type;
+    Vec* slice = reinterpret_cast<Vec*>(s_slice);
+    const int g = blockIdx.x, n = blockIdx.y;
+    const int ipp = p.cpg >> 2;                       // items per pixel
+    const int items = (int)p.HW * ipp;
+    const int cg0 = g * p.cpg;
+    auto unpack = [](const Vec& v, float (&f)[4]) {
+        if constexpr (IN_F32) { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+        else { const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y); f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; }
+    };
+    auto src_of = [&](int it) -> const Vec* {
+        const int pix = it / ipp, c = cg0 + (it - pix * ipp) * 4;
+        const long long row = (long long)n * p.HW + pix;
+        using Elem = typename std::conditional<IN_F32, float, __nv_bfloat16>::type;
+        const Elem* e = c < p.C1 ? reinterpret_cast<const Elem*>(p.x1) + row * p.C1 + c
+                                 : reinterpret_cast<const Elem*>(p.x2) + row * p.C2 + (c - p.C1);
+        return reinterpret_cast<const Vec*>(e);
+    };
+    float s = 0.f, ss = 0.f;
+    int it = threadIdx.x;
+    constexpr int UF = 8;                             // loads in flight per thread; accumulation stays in item order
+    for (; it < items; it += UF * 256) {
+        Vec v[UF];
+#pragma unroll
+        for (int u = 0; u < UF; ++u) {
+            if constexpr (IN_F32) v[u] = make_float4(0.f, 0.f, 0.f, 0.f); else v[u] = make_uint2(0u, 0u);
+            if (it + u * 256 < items) v[u] = *src_of(it + u * 256);
+        }
+#pragma unroll
+        for (int u = 0; u < UF; ++u) {
+            if (it + u * 256 < items) slice[it + u * 256] = v[u];
+            float f[4];
+            unpack(v[u], f);                          // slots past the end hold +0
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { s += f[i]; ss += f[i] * f[i]; }
+        }
     }
+    // fixed-order block reduction in fp64: butterfly inside each warp, the 8 warp sums added in warp order
+    double ds = s, dq = ss;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { ds += __shfl_xor_sync(0xffffffffu, ds, o); dq += __shfl_xor_sync(0xffffffffu, dq, o); }
+    if ((threadIdx.x & 31) == 0) { s_part[0][threadIdx.x >> 5] = ds; s_part[1][threadIdx.x >> 5] = dq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sum = 0.0, sq = 0.0;
+        for (int w = 0; w < 8; ++w) { sum += s_part[0][w]; sq += s_part[1][w]; }
+        const double inv_cnt = 1.0 / ((double)p.cpg * (double)p.HW);
+        const double m = sum * inv_cnt;
+        const double var = fmax(sq * inv_cnt - m * m, 0.0);
+        s_stat[0] = (float)m;
+        s_stat[1] = (float)(1.0 / sqrt(var + (double)p.eps));
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < p.cpg) {
+        const float sc = s_stat[1] * p.gamma[cg0 + threadIdx.x];
+        s_scale[threadIdx.x] = sc;
+        s_shift[threadIdx.x] = p.beta[cg0 + threadIdx.x] - s_stat[0] * sc;
+    }
+    __syncthreads();
+    for (it = threadIdx.x; it < items; it += 256) {
+        const int pix = it / ipp, j = (it - pix * ipp) * 4;
+        float f[4];
+        unpack(slice[it], f);
+        const long long o = ((long long)n * p.HW + pix) * p.C + cg0 + j;
+        if (p.raw) *reinterpret_cast<uint2*>(p.raw + o) = make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float y = f[i] * s_scale[j + i] + s_shift[j + i];
+            f[i] = p.silu ? silu_f(y) : y;
+        }
+        *reinterpret_cast<uint2*>(p.y + o) = make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
+    }
+}
+
+constexpr size_t kGnFusedMaxSmem = 96 * 1024;
+// the choice depends on (HW, C, groups, dtype) only -- never on N -- so batch invariance is kept
+static bool gn_use_fused(const rg_gn_t* g) {
+    const int C = g->C1 + g->C2;
+    if (C % g->groups) return false;
+    const int cpg = C / g->groups;
+    const size_t isz = g->in_dtype == RG_DT_F32 ? 4 : 2;
+    return g->HW <= 1024 && cpg % 4 == 0 && cpg <= 128 && (size_t)g->HW * cpg * isz <= kGnFusedMaxSmem;
 }
 
 static int fill_gn(const rg_gn_t* g, GnParams& p, dim3& grid, int& threads) {
@@ -208,9 +382,13 @@ static int fill_gn(const rg_gn_t* g, GnParams& p, dim3& grid, int& threads) {
     p.tpr = C / 8;
     p.rpb = 256 / p.tpr; if (p.rpb < 1) p.rpb = 1;
     threads = p.tpr * p.rpb;
+    if ((threads & ~31) < 4 * g->groups)
+        return set_error(RG_ERR_ARG, "groupnorm: needs 4 * groups <= the block's full warps (groups <= 32 for C = 320)");
     // The split depends on (HW, C) only -- never on N -- so an image's statistics are reduced in the same order
-    // whatever the batch size: at most RG_GN_MAX_BLOCKS blocks per image, at least 8 pixels per row slot.
-    long long ppb = (g->HW + RG_GN_MAX_BLOCKS - 1) / RG_GN_MAX_BLOCKS;
+    // whatever the batch size: 64 blocks per image (256 = RG_GN_MAX_BLOCKS for the VAE's >= 256x256-pixel levels, where 8
+    // images x 64 blocks would leave half of the SMs' thread slots empty), at least 8 pixels per row slot.
+    const long long max_blocks = g->HW >= 32768 ? RG_GN_MAX_BLOCKS : 64;
+    long long ppb = (g->HW + max_blocks - 1) / max_blocks;
     const long long min_ppb = 8LL * p.rpb;
     if (ppb < min_ppb) ppb = min_ppb;
     ppb = (ppb + p.rpb - 1) / p.rpb * p.rpb;
@@ -413,6 +591,32 @@ extern "C" int rg_groupnorm_apply(const rg_gn_t* g, rg_stream_t stream) {
     else gn_apply_kernel<false><<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     count_launch();
     return check_launch("gn_apply_kernel");
+}
+
+// GroupNorm in one call: the one-pass kernel where the (image, group) slice fits in shared memory, else stats + apply.
+extern "C" int rg_groupnorm(const rg_gn_t* g, rg_stream_t stream) {
+    if (g && g->groups > 0 && g->HW > 0 && gn_use_fused(g)) {
+        GnParams p; dim3 grid; int threads;
+        memset(&p, 0, sizeof(p));
+        int rc = fill_gn(g, p, grid, threads);
+        if (rc) return rc;
+        if (!g->y) return set_error(RG_ERR_ARG, "groupnorm: null output");
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(gn_fused_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnFusedMaxSmem);
+            cudaFuncSetAttribute(gn_fused_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnFusedMaxSmem);
+            attr_done = true;
+        }
+        const size_t smem = (size_t)p.HW * p.cpg * (p.in_f32 ? 4 : 2);
+        const dim3 fgrid((unsigned)p.groups, (unsigned)p.N);
+        if (p.in_f32) gn_fused_small_kernel<true><<<fgrid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+        else gn_fused_small_kernel<false><<<fgrid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+        count_launch();
+        return check_launch("gn_fused_small_kernel");
+    }
+    int rc = rg_groupnorm_stats(g, stream);
+    if (rc) return rc;
+    return rg_groupnorm_apply(g, stream);
 }
 
 template <bool IN_F32, int EPL>

@@ -119,12 +119,24 @@ def psnr_ssim_device(pred, gt, data_range: float = 255.0, K1: float = 0.01, K2: 
 
 
 class MetricsCalculator:
+    """``device`` "cuda" (any CUDA device string) scores PSNR / SSIM with the kernels of csrc/metrics.cu -- same float64
+    bits as "cpu" -- and raises if librestoragen.so or a GPU is missing (no silent fallback)."""
+
     def __init__(self, use_lpips: bool = True, use_fid: bool = False, device: str = "cpu",
                  lpips_fn: Callable[[np.ndarray, np.ndarray], float] | None = None):
         self.lpips_fn = lpips_fn
         self.use_lpips = use_lpips and lpips_fn is not None
         self.use_fid = False              # FID needs Inception weights that are not available offline
         self.device = device
+        self._gpu = str(device).startswith("cuda")
+
+    def _device_pair(self, pred: np.ndarray, gt: np.ndarray) -> tuple[float, float]:
+        import torch
+        pred = _match_shape(pred, gt)
+        p3, g3 = (pred[..., None], gt[..., None]) if gt.ndim == 2 else (pred, gt)
+        p, s = psnr_ssim_device(torch.from_numpy(np.ascontiguousarray(p3)[None]).to(self.device),
+                                torch.from_numpy(np.ascontiguousarray(g3)[None]).to(self.device))
+        return p[0], s[0]
 
     def calculate_psnr(self, pred: np.ndarray, gt: np.ndarray) -> float:
         return psnr(gt, _match_shape(pred, gt), data_range=255.0)
@@ -138,7 +150,11 @@ class MetricsCalculator:
         return float(self.lpips_fn(_match_shape(pred, gt), gt))
 
     def calculate_all(self, pred: np.ndarray, gt: np.ndarray) -> dict:
-        out = {"psnr": self.calculate_psnr(pred, gt), "ssim": self.calculate_ssim(pred, gt)}
+        if self._gpu:
+            p, s = self._device_pair(pred, gt)
+            out = {"psnr": p, "ssim": s}
+        else:
+            out = {"psnr": self.calculate_psnr(pred, gt), "ssim": self.calculate_ssim(pred, gt)}
         if self.use_lpips:
             out["lpips"] = self.calculate_lpips(pred, gt)
         return out

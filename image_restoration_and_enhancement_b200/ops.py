@@ -18,7 +18,7 @@ from ._lib import (RG_ACT_GEGLU, RG_ACT_NONE, RG_ACT_SILU, RG_DT_BF16, RG_DT_F16
 
 bf16, f32, f16 = torch.bfloat16, torch.float32, torch.float16
 GN_MAX_IMAGES = 1024      # RG_GN_MAX_IMAGES: fixed-size counter area in front of the GroupNorm workspace
-GN_MAX_BLOCKS = 64        # RG_GN_MAX_BLOCKS in include/restoragen.h
+GN_MAX_BLOCKS = 256       # RG_GN_MAX_BLOCKS in include/restoragen.h
 
 # When set to a list, conv2d / attention append (start_event, end_event, algorithmic_flops, kind) per launch
 # (bench.py's roofline leg); None in normal operation.
@@ -209,8 +209,7 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, grou
     p.gamma, p.beta, p.sums = gamma.data_ptr(), beta.data_ptr(), sums.data_ptr()
     p.y, p.raw, p.silu = y.data_ptr(), _ptr(raw), int(silu)
     e0 = _prof_begin()
-    check(lib.rg_groupnorm_stats(C.byref(p), _stream()), "rg_groupnorm_stats")
-    check(lib.rg_groupnorm_apply(C.byref(p), _stream()), "rg_groupnorm_apply")
+    check(lib.rg_groupnorm(C.byref(p), _stream()), "rg_groupnorm")      # one-pass kernel or stats + apply
     isz = x1.element_size()
     _prof_end(e0, float(N * H * W * Ct) * (2 * isz + 2 + (2 if want_raw else 0)), "groupnorm",
               f"N={N} HW={H * W} C={Ct} in={'f32' if isz == 4 else 'bf16'} silu={int(silu)} raw={int(want_raw)}")

@@ -136,7 +136,7 @@ int rg_softmax_rows(void* x, int64_t rows, int32_t cols, int64_t ld, rg_stream_t
  *   rg_groupnorm_stats is enqueued and are reset by the kernel, so a workspace zeroed once can be reused
  *   by every later call on the same stream.
  * ------------------------------------------------------------------------------------------- */
-#define RG_GN_MAX_BLOCKS 64
+#define RG_GN_MAX_BLOCKS 256
 #define RG_GN_MAX_IMAGES 1024   /* the counter area has a FIXED size so that one workspace serves any batch size */
 #define RG_GN_WORKSPACE_FLOATS(N, G) (RG_GN_MAX_IMAGES + (N) * (G) * 2 + (N) * RG_GN_MAX_BLOCKS * (G) * 2)
 
@@ -155,6 +155,10 @@ typedef struct rg_gn {
 
 int rg_groupnorm_stats(const rg_gn_t* p, rg_stream_t stream);
 int rg_groupnorm_apply(const rg_gn_t* p, rg_stream_t stream);
+/* both in one call.  When one (image, group) slice -- HW x C/groups elements -- fits in 96 KB of shared memory (the
+   32x32-and-below levels of the UNet) a single one-pass kernel reads the input once; otherwise stats + apply.  The
+   choice depends on (HW, C, groups, dtype) only, never on N, so results stay independent of the batch size. */
+int rg_groupnorm(const rg_gn_t* p, rg_stream_t stream);
 
 /* K8  LayerNorm over the last dim, affine, eps; x [rows][C] f32|bf16 -> y bf16 */
 int rg_layernorm(const void* x, int32_t in_dtype, int64_t rows, int32_t C, const float* gamma,

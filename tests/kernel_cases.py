@@ -395,7 +395,24 @@ def case_metrics(N=2, H=64, W=96, C=3, kind="noisy", seed=100):
     return float(bad), 0.0
 
 
+def case_metrics_calculator(seed=110):
+    """MetricsCalculator(device="cuda").calculate_all == the CPU calculator, including the cv2.resize of a prediction
+    whose shape differs from the ground truth (src/metrics.py:85-86) and 2-D (grayscale) inputs."""
+    import numpy as np
+    from image_restoration_and_enhancement_b200 import metrics
+    rng = np.random.default_rng(seed)
+    cpu, gpu = metrics.MetricsCalculator(use_lpips=False), metrics.MetricsCalculator(use_lpips=False, device="cuda")
+    bad = 0
+    for gshape, pshape in (((96, 80, 3), (96, 80, 3)), ((96, 80, 3), (48, 40, 3)), ((64, 64), (64, 64))):
+        gt = rng.integers(0, 256, gshape, dtype=np.uint8)
+        pred = rng.integers(0, 256, pshape, dtype=np.uint8)
+        a, b = cpu.calculate_all(pred, gt), gpu.calculate_all(pred, gt)
+        bad += sum(np.float64(a[k]).tobytes() != np.float64(b[k]).tobytes() for k in ("psnr", "ssim"))
+    return float(bad), 0.0
+
+
 CASES = {
+    "metrics_calculator_gpu": lambda: case_metrics_calculator(),
     # ---- CLIP text encoder pieces (causal attention on the tcgen05 kernel, embedding gather, quick_gelu)
     "attn_causal_clip_77": lambda: case_attention(B=2, heads=12, d=64, Nq=77, seed=120, causal=True),
     "attn_causal_multi_tile": lambda: case_attention(B=1, heads=3, d=64, Nq=300, seed=121, causal=True),
