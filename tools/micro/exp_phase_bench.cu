@@ -1,0 +1,66 @@
+// The softmax exp phase of the attention kernel in isolation: 128 fp32 scores per thread -> 64 packed fp16x2
+// probabilities.  One warp per SMSP (4 warps per SM), 148 SMs.  What does one warp need per 128-element row?
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <stdint.h>
+template <int MODE>
+__global__ void __launch_bounds__(128) k(const float* in, uint32_t* out, long long* cyc, int iters, float sl, float neg_m) {
+    float s[128];
+#pragma unroll
+    for (int i = 0; i < 128; ++i) s[i] = in[i * 128 + threadIdx.x % 128];
+    uint32_t acc = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        uint32_t pk[64];
+#pragma unroll
+        for (int i = 0; i < 128; i += 2) {
+            if (MODE == 0) {            // as in the kernel: 2 FFMA + cvt.f16x2 + ex2.f16x2
+                const float x0 = fmaf(s[i], sl, neg_m), x1 = fmaf(s[i + 1], sl, neg_m);
+                uint32_t h;
+                asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+                asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(pk[i / 2]) : "r"(h));
+            } else if (MODE == 1) {     // fp32 exponentials, then one pack: 2 FFMA + 2 ex2.f32 + cvt.f16x2
+                const float x0 = fmaf(s[i], sl, neg_m), x1 = fmaf(s[i + 1], sl, neg_m);
+                float e0, e1;
+                asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
+                asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+                asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk[i / 2]) : "f"(e1), "f"(e0));
+            } else if (MODE == 2) {     // no MUFU at all (FFMA + cvt): the issue-slot floor
+                const float x0 = fmaf(s[i], sl, neg_m), x1 = fmaf(s[i + 1], sl, neg_m);
+                asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk[i / 2]) : "f"(x1), "f"(x0));
+            } else {                    // MUFU only: 2 ex2.f32 per pair, no conversion
+                float e0, e1;
+                asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s[i]));
+                asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s[i + 1]));
+                pk[i / 2] = __float_as_uint(e0) ^ __float_as_uint(e1);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc ^= pk[i];
+        // make the next iteration depend on this one without adding work to the phase
+        neg_m += __uint_as_float((acc & 1u) << 23) * 1e-38f;
+    }
+    const long long t1 = clock64();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+int main() {
+    float* in; uint32_t* out; long long* cyc;
+    cudaMalloc(&in, 128 * 128 * 4); cudaMalloc(&out, 1 << 22); cudaMalloc(&cyc, 8);
+    cudaMemset(in, 0, 128 * 128 * 4);
+    const int iters = 200;
+    const char* names[] = {"2 FFMA + cvt.f16x2 + ex2.f16x2 (kernel)", "2 FFMA + 2 ex2.f32 + cvt.f16x2", "2 FFMA + cvt.f16x2 (no MUFU)", "2 ex2.f32 only"};
+    for (int mode = 0; mode < 4; ++mode)
+        for (int warps : {4, 8}) {
+            if (mode == 0) k<0><<<148, warps * 32>>>(in, out, cyc, iters, 0.25f, -1.0f);
+            else if (mode == 1) k<1><<<148, warps * 32>>>(in, out, cyc, iters, 0.25f, -1.0f);
+            else if (mode == 2) k<2><<<148, warps * 32>>>(in, out, cyc, iters, 0.25f, -1.0f);
+            else k<3><<<148, warps * 32>>>(in, out, cyc, iters, 0.25f, -1.0f);
+            cudaError_t e = cudaDeviceSynchronize();
+            long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+            printf("%-42s %d warp(s) per SMSP: %7.0f cycles per 128-element row per warp  (%s)\n", names[mode], warps / 4, (double)c / iters,
+                   cudaGetErrorString(e));
+        }
+    return 0;
+}
