@@ -72,7 +72,7 @@ struct AttnCfg {
     static constexpr int P_STRIDE = PSEP ? BKV / 2 : 0;
     static constexpr int O_COL = P_COL + 2 * P_STRIDE;
     static constexpr int TMEM_COLS = 512;
-    static constexpr int NBAR = 2 + 4 * SBUF + 4 + 3 * STAGES + 8;
+    static constexpr int NBAR = 2 + 4 * SBUF + 4 + 2 * STAGES;
     static_assert(O_COL + 2 * O_STRIDE <= 512, "TMEM budget");
     static_assert(NBAR * 8 + 8 <= 256, "barrier area");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -82,7 +82,7 @@ struct AttnCfg {
     static_assert(!PSEP || STAGES >= SBUF + 1, "SBUF tiles of score look-ahead need SBUF+1 K/V stages");
 };
 
-constexpr int kAttnThreads = 352;      // 8 softmax warps, 1 TMA warp, 2 MMA warps (one issuing lane per warpgroup)
+constexpr int kAttnThreads = 320;
 constexpr float kLazyRescale = 8.0f;       // raise the running max only when a tile exceeds it by > 2^8
 
 // All barrier phases are indexed by the CTA-global key-tile counter G = (items done) * n_kv + j, which is also the
@@ -101,20 +101,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     uint64_t* p_full = s_free + 2 * SBUF;              // [t]       P_t(G) stored, O_t rescaled     (softmax -> tensor core)
     uint64_t* pv_done = p_full + 2;                    // [t]       O_t += P_t(G) V retired         (tensor core -> softmax)
     uint64_t* kv_full = pv_done + 2; uint64_t* kv_empty = kv_full + STAGES;
-    uint64_t* v_ready = kv_empty + STAGES;             // [stage]   fp16 path: ones column patched into the landed V tile
-    uint64_t* exp_tok = v_ready + STAGES;              // [t][q]    warp q of warpgroup t may run its exponentials
-    uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(exp_tok + 8);
+    uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(kv_empty + STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kv = (p.Nk + BKV - 1) / BKV;
 
     if (warp == 8 && lane == 0) { tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap); }
     if (warp == 9 && lane == 0) {
-        mbar_init(&q_full, 1); mbar_init(&q_empty, 2);           // both MMA lanes release Q and the K/V stages
-        for (int i = 0; i < 2 * SBUF; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); }   // one arrival per warp
-        for (int t = 0; t < 2; ++t) { mbar_init(&p_full[t], 4); mbar_init(&pv_done[t], 1); }
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); mbar_init(&v_ready[s], 1); }
-        for (int i = 0; i < 8; ++i) mbar_init(&exp_tok[i], 1);
+        mbar_init(&q_full, 1); mbar_init(&q_empty, 1);
+        for (int i = 0; i < 2 * SBUF; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128); }
+        for (int t = 0; t < 2; ++t) { mbar_init(&p_full[t], 128); mbar_init(&pv_done[t], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&tmem_base_smem, Cfg::TMEM_COLS);
@@ -124,32 +121,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     const uint32_t tmem_base = tmem_base_smem;
 
     if (warp == 8) {
-        // ===================================================================== TMA producer (lane 0 issues).  fp16
-        // path: the whole warp also writes the ones column into every V tile once it has landed and hands the tile to
-        // the MMA lanes through v_ready -- off the tensor pipe's critical path.
-        auto patch_ones = [&](uint32_t G) {
-            mbar_wait(&kv_full[G % STAGES], (G / STAGES) & 1);
-            // V[k][d] = 1 for every key row k: column d sits in the TMA zero padding (atom d / 64, 16-byte chunk
-            // (d % 64) / 8 of the 128-byte row, SWIZZLE_128B: chunk ^= row & 7)
-            uint8_t* sv = sKV + (G % STAGES) * Cfg::STAGE_BYTES + Cfg::K_BYTES + (p.d >> 6) * Cfg::KV_ATOM_BYTES;
-            const int chunk = (p.d & 63) >> 3;
-            for (int k = lane; k < BKV; k += 32)
-                *reinterpret_cast<uint16_t*>(sv + k * 128 + ((chunk ^ (k & 7)) << 4)) = 0x3C00;   // fp16 1.0
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&v_ready[G % STAGES]);
-        };
-        constexpr uint32_t kPatchLag = STAGES >= 4 ? 2 : 1;
-        uint32_t g = 0, it = 0;                                         // g: K/V tiles requested so far (ring position)
-        uint32_t patched = 0;                                           // fp16: V tiles handed to the MMA lanes so far
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-            const int qp = item % p.n_qpairs, bh = item / p.n_qpairs;
-            const int h = bh % p.heads, b = bh / p.heads;
-            const int q0 = qp * 256;
-            // Q is released by the previous item's LAST score GEMMs, which need its last V tiles: hand those over first
-            if constexpr (F16) { while (patched < g) patch_ones(patched++); }
-            if (lane == 0) {
-                if (it > 0) mbar_wait(&q_empty, (it - 1) & 1);          // previous item's last S GEMMs have read Q
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            uint32_t g = 0, it = 0;                                     // g: K/V tiles loaded so far (ring position)
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+                const int qp = item % p.n_qpairs, bh = item / p.n_qpairs;
+                const int h = bh % p.heads, b = bh / p.heads;
+                const int q0 = qp * 256;
+                if (it > 0) mbar_wait(&q_empty, (it - 1) & 1);          // previous item's last S GEMM has read Q
                 mbar_expect_tx(&q_full, 2 * Cfg::Q_TILE_BYTES);
 #pragma unroll
                 for (int t = 0; t < 2; ++t)
@@ -157,12 +136,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                     for (int a = 0; a < DKA; ++a)
                         tma_load_4d(sQ + t * Cfg::Q_TILE_BYTES + a * 128 * 128, &p.qmap, &q_full, a * 64, h,
                                     q0 + t * 128, b);
-            }
-            for (int j = 0; j < n_kv; ++j, ++g) {
-                // patch first (a tile requested kPatchLag steps ago has landed), then refill the ring: the patch never
-                // waits behind kv_empty, and the refill never waits for a tile that is still in flight
-                if constexpr (F16) { if (patched + kPatchLag <= g) patch_ones(patched++); }
-                if (lane == 0) {
+                for (int j = 0; j < n_kv; ++j, ++g) {
                     const uint32_t stage = g % STAGES, phase = (g / STAGES) & 1;
                     mbar_wait(&kv_empty[stage], phase ^ 1);
                     uint8_t* sk = sKV + stage * Cfg::STAGE_BYTES;
@@ -174,97 +148,108 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                         tma_load_4d(sv + a * Cfg::KV_ATOM_BYTES, &p.vmap, &kv_full[stage], a * 64, h, j * BKV, b);
                     }
                 }
-                __syncwarp();
             }
         }
-        if constexpr (F16) { while (patched < g) patch_ones(patched++); }
-    } else if (warp >= 9) {
-        // ===================================================================== MMA issuers: lane 0 of warp 9 serves
-        // warpgroup 0, lane 0 of warp 10 serves warpgroup 1.  An issuing thread blocks while the tensor pipe's short
-        // queue is full and the pipe idles while its only issuer polls barriers, so with ONE issuer every barrier round
-        // trip of the loop was dead time for the pipe (measured: ~3300 cycles per 256-query x 128-key step against
-        // 1218 cycles for the same MMA sequence alone, tools/micro/mma_seq_bench.cu).  With one issuer per warpgroup
-        // the waits of one hide under the MMAs of the other.
-        if (lane == 0) {
-            const int t = warp - 9;
+    } else if (warp == 9) {
+        // ===================================================================== MMA issuer (lane 0 issues; the whole
+        // warp waits on the barriers and, for fp16, patches the ones column into each freshly landed V tile)
+        {
             // kind::f16 operand format: bits [7,10) A, [10,13) B: 0 = fp16, 1 = bf16
             constexpr uint32_t fmt_clear = F16 ? ~((7u << 7) | (7u << 10)) : ~0u;
             constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0) & fmt_clear;    // Q (K-major smem) x K (K-major smem)
             constexpr uint32_t idesc_o = umma_idesc_bf16(128, DV, 0, 1) & fmt_clear;     // P (TMEM)         x V (MN-major smem)
-            const uint32_t sq = smem_u32(sQ) + t * Cfg::Q_TILE_BYTES;
+            const uint32_t sq = smem_u32(sQ);
             const uint32_t skv = smem_u32(sKV);
-            const uint32_t p_tmem = PSEP ? tmem_base + Cfg::P_COL + t * Cfg::P_STRIDE : tmem_base + t * BKV;
-            const uint32_t o_tmem = tmem_base + Cfg::O_COL + t * Cfg::O_STRIDE;
-            // K_G has landed (and, fp16, the producer warp has patched the ones column into V_G)
             auto wait_kv = [&](uint32_t G) {
-                if constexpr (F16) mbar_wait(&v_ready[G % STAGES], (G / STAGES) & 1);
-                else mbar_wait(&kv_full[G % STAGES], (G / STAGES) & 1);
+                mbar_wait(&kv_full[G % STAGES], (G / STAGES) & 1);
+                if constexpr (F16) {
+                    // V[k][d] = 1 for every key row k: column d sits in the TMA zero padding (atom d / 64, 16-byte chunk
+                    // (d % 64) / 8 of the 128-byte row, SWIZZLE_128B: chunk ^= row & 7)
+                    uint8_t* sv = sKV + (G % STAGES) * Cfg::STAGE_BYTES + Cfg::K_BYTES + (p.d >> 6) * Cfg::KV_ATOM_BYTES;
+                    const int chunk = (p.d & 63) >> 3;
+                    for (int k = lane; k < BKV; k += 32)
+                        *reinterpret_cast<uint16_t*>(sv + k * 128 + ((chunk ^ (k & 7)) << 4)) = 0x3C00;   // fp16 1.0
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                }
                 tc_fence_after();
             };
             // S_t(G) = Q_t K_G^T
-            auto issue_s = [&](uint32_t G) {
+            auto issue_s = [&](int t, uint32_t G) {
                 const int buf = (int)(G % SBUF);
                 if (PSEP && G >= SBUF) {                         // the warpgroup has copied S_t(G-SBUF) out of this buffer
                     mbar_wait(&s_free[t * SBUF + buf], (G / SBUF - 1) & 1);
                     tc_fence_after();
                 }
                 const uint32_t sk = skv + (G % STAGES) * Cfg::STAGE_BYTES;
+                if (lane == 0) {
 #pragma unroll
-                for (int ks = 0; ks < DQK / 16; ++ks) {          // columns >= d are zero in both operands
-                    const uint64_t adesc = umma_desc_kmajor_sw128(sq + (ks / 4) * 128 * 128 + (ks % 4) * 32);
-                    const uint64_t bdesc = umma_desc_kmajor_sw128(sk + (ks / 4) * Cfg::KV_ATOM_BYTES + (ks % 4) * 32);
-                    umma_bf16(tmem_base + (t * SBUF + buf) * BKV, adesc, bdesc, idesc_s, ks != 0 ? 1u : 0u);
+                    for (int ks = 0; ks < DQK / 16; ++ks) {      // columns >= d are zero in both operands
+                        const uint64_t adesc = umma_desc_kmajor_sw128(sq + t * Cfg::Q_TILE_BYTES + (ks / 4) * 128 * 128 + (ks % 4) * 32);
+                        const uint64_t bdesc = umma_desc_kmajor_sw128(sk + (ks / 4) * Cfg::KV_ATOM_BYTES + (ks % 4) * 32);
+                        umma_bf16(tmem_base + (t * SBUF + buf) * BKV, adesc, bdesc, idesc_s, ks != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&s_full[t * SBUF + buf]);
                 }
-                umma_commit(&s_full[t * SBUF + buf]);
+                __syncwarp();
             };
             // O_t (+)= P_t(G) V_G
-            auto issue_pv = [&](uint32_t G, uint32_t acc) {
+            auto issue_pv = [&](int t, uint32_t G, uint32_t acc) {
                 mbar_wait(&p_full[t], G & 1);
                 tc_fence_after();
                 const uint32_t sv = skv + (G % STAGES) * Cfg::STAGE_BYTES + Cfg::K_BYTES;
+                const uint32_t p_tmem = PSEP ? tmem_base + Cfg::P_COL + t * Cfg::P_STRIDE : tmem_base + t * BKV;
+                if (lane == 0) {
 #pragma unroll
-                for (int ks = 0; ks < BKV / 16; ++ks) {
-                    // 16 kv rows per k-step = 2 groups of 8 rows (1024 B each); 64-wide d blocks are KV_ATOM_BYTES apart
-                    const uint64_t bdesc = umma_desc_mnmajor_sw128(sv + ks * 2048, Cfg::KV_ATOM_BYTES, 1024);
-                    // P: two 16-bit values per 32-bit TMEM column -> 16 keys = 8 columns
-                    umma_bf16_ts(o_tmem, p_tmem + ks * 8, bdesc, idesc_o, (acc | (uint32_t)ks) != 0 ? 1u : 0u);
+                    for (int ks = 0; ks < BKV / 16; ++ks) {
+                        // 16 kv rows per k-step = 2 groups of 8 rows (1024 B each); 64-wide d blocks are KV_ATOM_BYTES apart
+                        const uint64_t bdesc = umma_desc_mnmajor_sw128(sv + ks * 2048, Cfg::KV_ATOM_BYTES, 1024);
+                        // P: two 16-bit values per 32-bit TMEM column -> 16 keys = 8 columns
+                        umma_bf16_ts(tmem_base + Cfg::O_COL + t * Cfg::O_STRIDE, p_tmem + ks * 8, bdesc, idesc_o,
+                                     (acc | (uint32_t)ks) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&pv_done[t]);
                 }
-                umma_commit(&pv_done[t]);
+                __syncwarp();
             };
-            // q_empty and kv_empty expect one commit from each issuer: a commit tracks the issuing thread's own MMAs
+            auto commit = [&](uint64_t* bar) { if (lane == 0) umma_commit(bar); __syncwarp(); };
             uint32_t g0 = 0, it = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it, g0 += n_kv) {
                 mbar_wait(&q_full, it & 1);
                 tc_fence_after();
                 if constexpr (!PSEP) {
                     wait_kv(g0);
-                    issue_s(g0);
-                    if (n_kv == 1) umma_commit(&q_empty);
+                    issue_s(0, g0); issue_s(1, g0);
+                    if (n_kv == 1) commit(&q_empty);
                     for (int j = 0; j < n_kv; ++j) {
                         const uint32_t G = g0 + j;
-                        issue_pv(G, j > 0 ? 1u : 0u);
-                        umma_commit(&kv_empty[G % STAGES]);          // K_G / V_G consumed once these retire
-                        if (j + 1 < n_kv) {                          // in order behind P_t(G) V: P aliases S_t
-                            wait_kv(G + 1);
-                            issue_s(G + 1);
-                            if (j + 2 == n_kv) umma_commit(&q_empty);
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            issue_pv(t, G, j > 0 ? 1u : 0u);
+                            if (t == 1) commit(&kv_empty[G % STAGES]);   // K_G / V_G consumed once these retire
+                            if (j + 1 < n_kv) {                               // in order behind P_t(G) V: P aliases S_t
+                                if (t == 0) wait_kv(G + 1);
+                                issue_s(t, G + 1);
+                                if (t == 1 && j + 2 == n_kv) commit(&q_empty);
+                            }
                         }
                     }
                 } else {
-                    for (int j = 0; j < SBUF && j < n_kv; ++j) {     // SBUF score tiles of look-ahead
+                    for (int j = 0; j < SBUF && j < n_kv; ++j) {              // SBUF score tiles of look-ahead
                         wait_kv(g0 + j);
-                        issue_s(g0 + j);
-                        if (j + 1 == n_kv) umma_commit(&q_empty);
+                        issue_s(0, g0 + j); issue_s(1, g0 + j);
+                        if (j + 1 == n_kv) commit(&q_empty);
                     }
                     for (int j = 0; j < n_kv; ++j) {
                         const uint32_t G = g0 + j;
                         if (j + SBUF < n_kv) {
                             wait_kv(G + SBUF);
-                            issue_s(G + SBUF);
-                            if (j + SBUF + 1 == n_kv) umma_commit(&q_empty);
+                            issue_s(0, G + SBUF); issue_s(1, G + SBUF);
+                            if (j + SBUF + 1 == n_kv) commit(&q_empty);
                         }
-                        issue_pv(G, j > 0 ? 1u : 0u);
-                        umma_commit(&kv_empty[G % STAGES]);
+                        issue_pv(0, G, j > 0 ? 1u : 0u);
+                        issue_pv(1, G, j > 0 ? 1u : 0u);
+                        commit(&kv_empty[G % STAGES]);
                     }
                 }
             }
@@ -303,8 +288,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                 RG_STAMP(2);
                 if constexpr (PSEP) {                            // the buffer can take S_t(G+SBUF) now
                     tc_fence_before();
-                    __syncwarp();                                // one arrival per warp
-                    if (lane == 0) mbar_arrive(&s_free[t * SBUF + buf]);
+                    mbar_arrive(&s_free[t * SBUF + buf]);
                 }
                 const int kv_left = p.Nk - j * BKV;              // columns >= kv_left are padding
                 if (kv_left < BKV) {                             // warp-uniform: only the last tile can be ragged
@@ -353,14 +337,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                         }
                     }
                 }
-#ifndef RG_ATTN_NO_ANTI
-                // Warp q of either warpgroup sits on SMSP q and shares its MUFU pipe.  Left alone the two fall into
-                // lock-step: both run their exponentials together at half rate and then do their bookkeeping together
-                // while the pipe idles.  They take turns instead: a warp starts its exponentials when its partner has
-                // finished, so one's bookkeeping hides under the other's exponentials.  One arrival, one waiting warp.
-                if (t == 0) { if (G > 0) mbar_wait(&exp_tok[qd], (G - 1) & 1); }
-                else mbar_wait(&exp_tok[4 + qd], G & 1);
-#endif
                 RG_STAMP(3);
                 const float neg_m = -m_run;
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
@@ -390,10 +366,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                             tmem_st16(p_tmem + (i - 28) / 2, reinterpret_cast<uint32_t (&)[16]>(pk[(i - 28) / 2]));
                     }
                 }
-#ifndef RG_ATTN_NO_ANTI
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&exp_tok[(1 - t) * 4 + qd]);
-#endif
                 RG_STAMP(4);
                 if constexpr (PSEP) {
                     if (!quiescent) { mbar_wait(&pv_done[t], (G - 1) & 1); tc_fence_after(); }
@@ -405,8 +377,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                 tmem_st_wait();
                 RG_STAMP(6);
                 tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&p_full[t]);
+                mbar_arrive(&p_full[t]);
                 RG_STAMP(7);
             }
             // ---- item epilogue: O_t / l -> bf16 -> global
