@@ -30,10 +30,19 @@ elif which == "attn":        # self-attention at 64x64 latents: B=16, 8 heads, d
     qkv = torch.randn((16, 4096, 3, 8, 40), device="cuda").to(torch.bfloat16)
     for _ in range(3):
         ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], 40 ** -0.5)
-elif which == "gn":
+elif which == "gn":          # GroupNorm+SiLU: UNet 64x64x320 fp32 (stats + apply), VAE 512x512x128 bf16, UNet 16x16x1280 (one pass)
+    g = torch.ones(1280, device="cuda"); bta = torch.zeros(1280, device="cuda")
     x = torch.randn((16, 64, 64, 320), device="cuda")
+    xv = torch.randn((8, 512, 512, 128), device="cuda").to(torch.bfloat16)
+    xs = torch.randn((16, 16, 16, 1280), device="cuda")
+    for _ in range(2):
+        ops.groupnorm(x, g[:320].contiguous(), bta[:320].contiguous(), silu=True)
+        ops.groupnorm(xv, g[:128].contiguous(), bta[:128].contiguous(), eps=1e-6, silu=True)
+        ops.groupnorm(xs, g, bta, silu=True)
+elif which == "ln":          # LayerNorm 65536 x 320 fp32 -> bf16
+    x = torch.randn((65536, 320), device="cuda")
     g = torch.ones(320, device="cuda"); bta = torch.zeros(320, device="cuda")
     for _ in range(3):
-        ops.groupnorm(x, g, bta, silu=True)
+        ops.layernorm(x, g, bta)
 torch.cuda.synchronize()
 print("done", which)
