@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const GnParams p) {
     long long pix = p0 + tr;
     // U independent loads in flight per thread (8 x 16 B for bf16, 4 x 32 B for fp32); the accumulation below is in
     // pixel order, exactly the order of the scalar tail loop, so the unroll factor does not change a single bit
-    constexpr int U = IN_F32 ? 4 : 8;
+    constexpr int U = 8;
     for (; pix < p1; pix += (long long)U * p.rpb) {
         // ragged end: slots past the slice load nothing and contribute +0 (no serial tail loop -- its dependent
         // load -> add chain cost one full memory latency per pixel)

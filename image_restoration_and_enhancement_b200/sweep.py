@@ -54,7 +54,7 @@ def _score(preds: list[np.ndarray], gts: list[np.ndarray], backend: str) -> tupl
 
 
 def run_task(pipe, task: str, n_images: int, rank: int = 0, world: int = 1, size: int = 512, batch: int | None = None,
-             handoff_mode: str = "memory", metrics_backend: str = "gpu", workdir=None
+             handoff_mode: str = "memory", metrics_backend: str = "gpu", workdir=None, overlap: bool = True
              ) -> tuple[list[int], dict[str, list[float]], float]:
     """Predict + score this rank's share of one task.
 
@@ -64,21 +64,25 @@ def run_task(pipe, task: str, n_images: int, rank: int = 0, world: int = 1, size
                re-read, like the ground truth, with cv2.imread;
       "memory" the same encoders / decoders on byte buffers (identical arrays, no file system);
       "none"   raw arrays straight through (no codec; NOT what the reference's evaluator scores for .jpg tasks).
+    ``overlap``: prepare batch k+1 and score batch k-1 on host threads while the GPU samples batch k.
     """
+    from concurrent.futures import ThreadPoolExecutor
     from pathlib import Path
     from . import handoff
     mine = shard(n_images, rank, world)
     bsz = batch or BATCH[task]
     tdir = TASK_DIR[task]
-    vals: dict[str, list[float]] = {"psnr": [], "ssim": []}
+    if handoff_mode not in ("none", "memory", "disk"):
+        raise ValueError(f"unknown handoff_mode {handoff_mode}")
     if handoff_mode == "disk":
         if workdir is None:
             raise ValueError('handoff_mode="disk" needs workdir')
         pair_root, pred_dir = Path(workdir) / "pairs", Path(workdir) / "predictions" / tdir / "test"
         pred_dir.mkdir(parents=True, exist_ok=True)
-    t0 = time.time()
-    for s in range(0, len(mine), bsz):
-        idx = mine[s:s + bsz]
+    device = torch.cuda.current_device() if (metrics_backend == "gpu" and torch.cuda.is_available()) else None
+
+    def prepare(idx):
+        """Host side of one batch before the sampling run: synthesis + the dataset codecs (no CUDA)."""
         items = [synth.make_pair(task, i, size, size) for i in idx]
         names = [handoff.input_name(tdir, i) for i in idx]
         masks = None
@@ -94,7 +98,7 @@ def run_task(pipe, task: str, n_images: int, rank: int = 0, world: int = 1, size
             gts = [handoff.roundtrip_dataset_image(it["gt"], handoff.gt_name(tdir, i), "cv2") for it, i in zip(items, idx)]
             if "mask" in items[0]:
                 masks = [handoff.roundtrip_dataset_image(it["mask"], nm, "pil_l") for it, nm in zip(items, names)]
-        elif handoff_mode == "disk":
+        else:
             for it, i in zip(items, idx):
                 handoff.write_pairs(pair_root, tdir, i, it)
             base = pair_root / tdir / "test"
@@ -102,9 +106,12 @@ def run_task(pipe, task: str, n_images: int, rank: int = 0, world: int = 1, size
             gts = [handoff.load_image(base / "gt" / handoff.gt_name(tdir, i)) for i in idx]
             if "mask" in items[0]:
                 masks = [Image.open(base / "mask" / nm).convert("L") for nm in names]    # generate_predictions.py:74
-        else:
-            raise ValueError(f"unknown handoff_mode {handoff_mode}")
-        outs = pipe.process_batch(ims, task, masks=masks)
+        return names, ims, gts, masks
+
+    def score(outs, names, gts):
+        """Host side after the sampling run: the prediction hand-off, then the metrics."""
+        if device is not None:
+            torch.cuda.set_device(device)
         if handoff_mode == "none":
             preds = [np.array(o.convert("RGB")) for o in outs]
         elif handoff_mode == "memory":
@@ -113,9 +120,39 @@ def run_task(pipe, task: str, n_images: int, rank: int = 0, world: int = 1, size
             for o, nm in zip(outs, names):
                 handoff.save_prediction(o, pred_dir / nm)                                # generate_predictions.py:83-84
             preds = [handoff.load_image(pred_dir / nm) for nm in names]
-        p, q = _score(preds, gts, metrics_backend)
-        vals["psnr"] += p
-        vals["ssim"] += q
+        return _score(preds, gts, metrics_backend)
+
+    batches = [mine[s:s + bsz] for s in range(0, len(mine), bsz)]
+    vals: dict[str, list[float]] = {"psnr": [], "ssim": []}
+    t0 = time.time()
+    if not overlap or len(batches) < 2:
+        for idx in batches:
+            names, ims, gts, masks = prepare(idx)
+            p, q = score(pipe.process_batch(ims, task, masks=masks), names, gts)
+            vals["psnr"] += p
+            vals["ssim"] += q
+        return mine, vals, time.time() - t0
+    # Software pipeline over batches: while the GPU samples batch k, one host thread prepares batch k+1 (synthesis,
+    # codecs) and another scores batch k-1 (codec round trip, metric kernels on the default stream).  PIL / OpenCV /
+    # numpy release the GIL, so the three stages really overlap; results are collected in batch order.
+    with ThreadPoolExecutor(max_workers=2) as pool:
+        pending = []
+        nxt = pool.submit(prepare, batches[0])
+        last_n = None
+        for k, idx in enumerate(batches):
+            names, ims, gts, masks = nxt.result()
+            if k + 1 < len(batches):
+                nxt = pool.submit(prepare, batches[k + 1])
+            if last_n is not None and len(idx) != last_n:
+                for f in pending:            # a new batch size captures a new CUDA graph: no concurrent CUDA work then
+                    f.result()
+            last_n = len(idx)
+            outs = pipe.process_batch(ims, task, masks=masks)
+            pending.append(pool.submit(score, outs, names, gts))
+        for f in pending:
+            p, q = f.result()
+            vals["psnr"] += p
+            vals["ssim"] += q
     return mine, vals, time.time() - t0
 
 

@@ -77,6 +77,8 @@ def test_sweep_disk_flow_equals_memory_flow(tmp_path, task):
     idx_m, mem, _ = sweep.run_task(pipe, task, 5, size=64, batch=2, handoff_mode="memory", metrics_backend="cpu")
     assert idx_d == idx_m == [0, 1, 2, 3, 4]
     assert disk == mem                                      # float64 equality, value by value
+    _, serial, _ = sweep.run_task(pipe, task, 5, size=64, batch=2, handoff_mode="memory", metrics_backend="cpu", overlap=False)
+    assert serial == mem                                    # the host/GPU software pipeline does not change a value
     # ... and equals the reference's directory-based evaluation of the files just written
     ev = metrics.evaluate_task(tmp_path / "predictions" / sweep.TASK_DIR[task] / "test",
                                tmp_path / "pairs" / sweep.TASK_DIR[task] / "test" / "gt", task, use_lpips=False)

@@ -28,10 +28,12 @@ for task in ("denoise", "colorize", "inpaint", "sr"):
     sweep.run_task(pipe, task, 8, handoff_mode="none", metrics_backend="gpu")          # warm-up: weights, graphs
     res = {}
     with tempfile.TemporaryDirectory() as tmp:
-        for mode, backend in (("memory", "gpu"), ("memory", "cpu"), ("disk", "cpu"), ("none", "gpu")):
-            _, vals, secs = sweep.run_task(pipe, task, n, handoff_mode=mode, metrics_backend=backend, workdir=tmp)
-            res[(mode, backend)] = vals
-            say(f"{task:9s} handoff={mode:6s} metrics={backend}: {secs:7.2f} s for {n} images = {n / secs:6.2f} img/s   "
+        for mode, backend, ov in (("memory", "gpu", True), ("memory", "gpu", False), ("memory", "cpu", False), ("disk", "cpu", False),
+                                  ("none", "gpu", False)):
+            _, vals, secs = sweep.run_task(pipe, task, n, handoff_mode=mode, metrics_backend=backend, workdir=tmp, overlap=ov)
+            res[(mode, backend)] = vals if (mode, backend) not in res else res[(mode, backend)]
+            assert res[(mode, backend)] == vals
+            say(f"{task:9s} handoff={mode:6s} metrics={backend} overlap={int(ov)}: {secs:7.2f} s for {n} images = {n / secs:6.2f} img/s   "
                 f"psnr[0]={vals['psnr'][0]!r} ssim[0]={vals['ssim'][0]!r}")
     same_backend = res[("memory", "gpu")] == res[("memory", "cpu")]
     same_handoff = res[("memory", "cpu")] == res[("disk", "cpu")]
