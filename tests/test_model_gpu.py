@@ -122,3 +122,35 @@ def test_checkpoint_directory_roundtrip(tmp_path):
     (tmp_path / "best" / "vae" / "diffusion_pytorch_model.safetensors").unlink()
     with pytest.raises(OSError):                                             # incomplete directory (src/inference.py:227)
         StableDiffusionImg2ImgPipeline.from_pretrained(str(tmp_path / "best"))
+
+
+def test_training_validation_caller(tmp_path):
+    """SURVEY 8f "f4", second half: scripts/train_denoising.py run_validation against the B200 pipeline -- the UNet under
+    training is assigned to ``pipeline.unet`` (a torch module with diffusers key names: here the oracle UNet with other
+    weights) and the samples must be those of a pipeline built directly from that state dict."""
+    from image_restoration_and_enhancement_b200 import validation
+    from image_restoration_and_enhancement_b200.pipelines import StableDiffusionImg2ImgPipeline, _Tokenizer, make_text_encoder
+    from image_restoration_and_enhancement_b200.schedulers import SCHEDULERS
+    mc.case_pipeline("denoise")                                             # builds and caches the seed-0 pipeline
+    pipe = mc._cache[("pipe", "img2img", 0)]
+    trained, tsd = mc.oracle_unet(4, 7)                                      # "the model being trained": different weights
+    vsd = mc.oracle_vae(1)[1]
+
+    def item(i):
+        gt = torch.from_numpy(mc.synth_image(40 + i, 256, 256)).permute(2, 0, 1).float() / 127.5 - 1.0
+        g = torch.Generator().manual_seed(i)
+        return {"input": (gt + 0.05 * torch.randn(gt.shape, generator=g)).clamp(-1, 1), "gt": gt, "sigma": 6.4 + i}
+    ds = [item(i) for i in range(5)]
+    out = validation.run_validation(0, ds, pipe, trained, tmp_path, num_samples=3)
+    assert out["num_samples"] == 3 and set(out["by_sigma"]) == {6, 8, 10}      # indices 0, 2, 4 -> sigma 6.4, 8.4, 10.4
+    assert len(list((tmp_path / "val_samples").glob("epoch_1_sample_*_idx*.png"))) == 3
+    assert np.isfinite(out["psnr"]) and 0 <= out["ssim_y"] <= 1
+    # same weights loaded the ordinary way give the same per-image metrics, bit for bit
+    direct = StableDiffusionImg2ImgPipeline(dict(tsd), dict(vsd), SCHEDULERS["PNDMScheduler"](), make_text_encoder(2),
+                                            _Tokenizer(None)).to("cuda")
+    ref = validation.run_validation(0, ds, direct, None, tmp_path / "direct", num_samples=3)
+    assert ref["per_image"] == out["per_image"]
+    # and they differ from what the seed-0 weights produced before the assignment
+    pipe.unet = mc.oracle_unet(4, 0)[0]                                      # restore for the other tests of this process
+    back = validation.run_validation(0, ds, pipe, None, tmp_path / "back", num_samples=3)
+    assert back["per_image"] != out["per_image"]

@@ -28,6 +28,7 @@ def main():
         "vibrant realistic natural colors, colorful, high quality photo, detailed, full color, rich colors",  # :89
         "high quality detailed photo",                                             # :90
         "high quality detailed photo, realistic",                                  # app.py:272
+        "a photograph, high quality, detailed, sharp",                             # scripts/train_denoising.py:399 (validation)
         "",                                                                        # CFG negative prompt
     ]
     ids = {p: tok(p, padding="max_length", max_length=77, truncation=True)["input_ids"] for p in prompts}
