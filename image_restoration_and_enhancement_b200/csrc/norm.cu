@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const GnParams p) {
 }
 
 template <bool IN_F32>
-__global__ void __launch_bounds__(512) gn_apply_kernel(const GnParams p) {
+__global__ void __launch_bounds__(512, IN_F32 ? 2 : 1) gn_apply_kernel(const GnParams p) {
     const int n = blockIdx.y;
     const int tc = threadIdx.x % p.tpr, tr = threadIdx.x / p.tpr;
     if (tr >= p.rpb) return;
