@@ -403,7 +403,7 @@ static int fill_gn(const rg_gn_t* g, GnParams& p, dim3& grid, int& threads) {
 // already in flight while the current one is reduced (the kernel is a pure HBM stream: fp32 in, bf16 out).
 // EPL = elements per lane = C / 32 (10 / 20 / 40 for SD-1.5), loaded as EPL/VEC vectors of VEC floats.
 template <bool IN_F32, int EPL>
-__global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ x_, long long rows,
+__global__ void __launch_bounds__(256, EPL <= 10 ? 4 : 0) layernorm_kernel(const void* __restrict__ x_, long long rows,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, __nv_bfloat16* __restrict__ y) {
     constexpr int C = EPL * 32;
