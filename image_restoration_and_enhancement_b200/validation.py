@@ -31,8 +31,10 @@ def _to_u8(t: torch.Tensor) -> np.ndarray:
 
 def run_validation(epoch: int, val_dataset, pipeline, unet_model, output_dir, num_samples: int = 4,
                    device: str = "cuda", prompt: str = VALIDATION_PROMPT, strength: float = 0.3,
-                   num_inference_steps: int = 20, guidance_scale: float = 5.0) -> dict | None:
-    """Returns {'psnr', 'ssim', 'psnr_y', 'ssim_y', 'by_sigma', 'num_samples'} or None if there is nothing to validate."""
+                   num_inference_steps: int = 20, guidance_scale: float = 5.0, seed: int | None = None) -> dict | None:
+    """Returns {'psnr', 'ssim', 'psnr_y', 'ssim_y', 'by_sigma', 'num_samples'} or None if there is nothing to validate.
+    ``seed``: the reference draws its noise from the global RNG (no generator is passed, ``:400-406``), so its validation
+    numbers are not reproducible; with a seed every sample gets ``torch.Generator(device).manual_seed(seed)``."""
     import cv2
     if val_dataset is None or len(val_dataset) == 0:
         logger.warning("Validation dataset is None or empty, skipping validation")
@@ -56,8 +58,9 @@ def run_validation(epoch: int, val_dataset, pipeline, unet_model, output_dir, nu
             for i, idx in enumerate(sample_indices):
                 sample = val_dataset[int(idx)]
                 input_np, gt_np = _to_u8(sample["input"]), _to_u8(sample["gt"])
+                extra = {} if seed is None else {"generator": torch.Generator(device=device).manual_seed(seed)}
                 result = pipeline(prompt=prompt, image=Image.fromarray(input_np), strength=strength,
-                                  num_inference_steps=num_inference_steps, guidance_scale=guidance_scale).images[0]
+                                  num_inference_steps=num_inference_steps, guidance_scale=guidance_scale, **extra).images[0]
                 result_np = np.array(result)
                 if result_np.sum() < 1000:
                     logger.warning(f"Sample {idx} produced dark output (sum={result_np.sum()})")

@@ -141,16 +141,18 @@ def test_training_validation_caller(tmp_path):
         g = torch.Generator().manual_seed(i)
         return {"input": (gt + 0.05 * torch.randn(gt.shape, generator=g)).clamp(-1, 1), "gt": gt, "sigma": 6.4 + i}
     ds = [item(i) for i in range(5)]
-    out = validation.run_validation(0, ds, pipe, trained, tmp_path, num_samples=3)
+    out = validation.run_validation(0, ds, pipe, trained, tmp_path, num_samples=3, seed=123)
     assert out["num_samples"] == 3 and set(out["by_sigma"]) == {6, 8, 10}      # indices 0, 2, 4 -> sigma 6.4, 8.4, 10.4
     assert len(list((tmp_path / "val_samples").glob("epoch_1_sample_*_idx*.png"))) == 3
     assert np.isfinite(out["psnr"]) and 0 <= out["ssim_y"] <= 1
     # same weights loaded the ordinary way give the same per-image metrics, bit for bit
     direct = StableDiffusionImg2ImgPipeline(dict(tsd), dict(vsd), SCHEDULERS["PNDMScheduler"](), make_text_encoder(2),
                                             _Tokenizer(None)).to("cuda")
-    ref = validation.run_validation(0, ds, direct, None, tmp_path / "direct", num_samples=3)
+    ref = validation.run_validation(0, ds, direct, None, tmp_path / "direct", num_samples=3, seed=123)
     assert ref["per_image"] == out["per_image"]
     # and they differ from what the seed-0 weights produced before the assignment
     pipe.unet = mc.oracle_unet(4, 0)[0]                                      # restore for the other tests of this process
-    back = validation.run_validation(0, ds, pipe, None, tmp_path / "back", num_samples=3)
+    back = validation.run_validation(0, ds, pipe, None, tmp_path / "back", num_samples=3, seed=123)
+    unseeded = validation.run_validation(0, ds, pipe, None, tmp_path / "unseeded", num_samples=2)      # the reference's way
+    assert unseeded["num_samples"] == 2
     assert back["per_image"] != out["per_image"]
