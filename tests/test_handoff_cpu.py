@@ -86,3 +86,65 @@ def test_sweep_disk_flow_equals_memory_flow(tmp_path, task):
     assert ev["metrics"]["psnr"]["mean"] == np.mean(mem["psnr"]) and ev["metrics"]["ssim"]["median"] == np.median(mem["ssim"])
     _, raw, _ = sweep.run_task(pipe, task, 5, size=64, batch=2, handoff_mode="none", metrics_backend="cpu")
     assert raw != mem                                       # codecs on both sides change what is scored
+
+
+class _StubSDPipeline:
+    """Quacks like the object scripts/train_denoising.py hands to run_validation: .to, .unet/.vae/.text_encoder with
+    eval/train, settable safety attributes, __call__ -> .images."""
+
+    class _Mod:
+        def __init__(self):
+            self.mode = "train"
+
+        def eval(self):
+            self.mode = "eval"
+            return self
+
+        def train(self, mode=True):
+            self.mode = "train"
+            return self
+
+    def __init__(self):
+        self.unet, self.vae, self.text_encoder = self._Mod(), self._Mod(), self._Mod()
+        self.safety_checker, self.feature_extractor, self.requires_safety_checker = object(), object(), True
+        self.calls = []
+
+    def to(self, device):
+        return self
+
+    def __call__(self, prompt, image, strength, num_inference_steps, guidance_scale, **kw):
+        import cv2
+        self.calls.append((prompt, strength, num_inference_steps, guidance_scale, self.unet.mode))
+        out = cv2.blur(np.array(image), (3, 3))
+        return type("Out", (), {"images": [Image.fromarray(out)]})()
+
+
+def test_run_validation_bookkeeping_cpu(tmp_path):
+    """validation.run_validation (mirror of scripts/train_denoising.py:328-520) with a stand-in pipeline: sample
+    selection, call parameters, Y-channel metrics, sigma buckets, comparison strips, module modes."""
+    import cv2
+    import torch
+    from image_restoration_and_enhancement_b200 import validation
+
+    def item(i):
+        gt = torch.from_numpy(synth.clean_image(i, 64, 64)).permute(2, 0, 1).float() / 127.5 - 1.0
+        return {"input": (gt + 0.04 * torch.randn(gt.shape, generator=torch.Generator().manual_seed(i))).clamp(-1, 1),
+                "gt": gt, "sigma": 5.2 + i}
+    ds = [item(i) for i in range(7)]
+    pipe, trained = _StubSDPipeline(), _StubSDPipeline._Mod()
+    out = validation.run_validation(2, ds, pipe, trained, tmp_path, num_samples=4, device="cpu")
+    assert pipe.unet is trained and trained.mode == "train"                # swapped in, evaluated in eval mode, flipped back
+    assert [c[4] for c in pipe.calls] == ["eval"] * 4
+    assert all(c[:4] == (validation.VALIDATION_PROMPT, 0.3, 20, 5.0) for c in pipe.calls)
+    assert pipe.safety_checker is None and pipe.requires_safety_checker is False
+    assert out["num_samples"] == 4 and sorted(out["by_sigma"]) == [5, 7, 9, 11]     # indices 0, 2, 4, 6
+    files = sorted(p.name for p in (tmp_path / "val_samples").glob("*.png"))
+    assert files == [f"epoch_3_sample_{k + 1}_idx{i}.png" for k, i in enumerate((0, 2, 4, 6))]
+    assert Image.open(tmp_path / "val_samples" / files[0]).size == (3 * 64, 64)      # input | result | gt
+    # first sample recomputed by hand
+    inp, gt = validation._to_u8(ds[0]["input"]), validation._to_u8(ds[0]["gt"])
+    res = cv2.blur(inp, (3, 3))
+    assert out["per_image"]["psnr"][0] == metrics.psnr(gt, res) and out["per_image"]["ssim"][0] == metrics.ssim(gt, res)
+    y = lambda a: cv2.cvtColor(a, cv2.COLOR_RGB2YCrCb)[:, :, 0]
+    assert out["by_sigma"][5]["psnr_y"] == metrics.psnr(y(gt), y(res))
+    assert validation.run_validation(0, [], pipe, None, tmp_path) is None
