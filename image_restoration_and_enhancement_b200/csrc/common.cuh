@@ -223,8 +223,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
 }
+// Arrival on a barrier of another CTA of the cluster (shared::cluster address from mapa).  Default semantics
+// (.release.cta): the barrier hands over a TMEM accumulator slot, whose reads were completed by tcgen05.wait::ld and
+// ordered by tcgen05.fence::before_thread_sync -- no global data travels through it.  The .release.cluster form compiles
+// to MEMBAR.ALL.GPU + ERRBAR in front of the arrive, which was 28 % of all stall samples of the short-K GEMMs
+// (profiles/r01_ncu_geglu_z.txt).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA tile load of one CTA of a pair: data lands in this CTA's shared memory, completion bytes are signalled on
 // an mbarrier given as a shared::cluster address (the leader CTA's barrier).

@@ -11,8 +11,13 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
+import os
+
 import torch
 
+from image_restoration_and_enhancement_b200 import _lib
+if os.environ.get("RG_LIB"):            # another build of the library, for same-box A/B runs
+    _lib.LIB_PATH = Path(os.environ["RG_LIB"]).resolve()
 from image_restoration_and_enhancement_b200 import ops, synth
 from image_restoration_and_enhancement_b200.pipelines import StableDiffusionImg2ImgPipeline
 

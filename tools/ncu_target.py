@@ -26,6 +26,13 @@ elif which == "qkv":         # q|k|v projection at 64x64 latents: M=65536, N=960
     w = (torch.randn((960, 320), device="cuda") / 18.0).to(torch.bfloat16)
     for _ in range(4):
         ops.linear(x, w, out_bf16=True)
+elif which == "geglu":       # ff.net.0 at 64x64 latents: M=65536, N=2560 (-> 1280 after GEGLU), K=320: the largest transformer GEMM
+    from image_restoration_and_enhancement_b200._lib import RG_ACT_GEGLU
+    x = torch.randn((65536, 320), device="cuda").to(torch.bfloat16)
+    w = (torch.randn((2560, 320), device="cuda") / 18.0).to(torch.bfloat16)
+    b = torch.randn((2560,), device="cuda")
+    for _ in range(3):
+        ops.linear(x, w, bias=b, act=RG_ACT_GEGLU, out_bf16=True)
 elif which == "attn":        # self-attention at 64x64 latents: B=16, 8 heads, d=40, N=4096
     qkv = torch.randn((16, 4096, 3, 8, 40), device="cuda").to(torch.bfloat16)
     for _ in range(3):
