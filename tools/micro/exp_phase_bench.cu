@@ -1,10 +1,11 @@
 // The softmax exp phase of the attention kernel in isolation: 128 fp32 scores per thread -> 64 packed fp16x2
-// probabilities.  One warp per SMSP (4 warps per SM), 148 SMs.  What does one warp need per 128-element row?
+// probabilities.  One or two warps per SMSP (4 / 8 warps per SM), 148 SMs.  What does one warp need per 128-element row?
+// (measured with one warp per SMSP: 1342 cycles for the f16x2 form, 1112 for two fp32 exponentials + one pack)
 #include <cstdio>
 #include <cuda_runtime.h>
 #include <stdint.h>
 template <int MODE>
-__global__ void __launch_bounds__(128) k(const float* in, uint32_t* out, long long* cyc, int iters, float sl, float neg_m) {
+__global__ void __launch_bounds__(256) k(const float* in, uint32_t* out, long long* cyc, int iters, float sl, float neg_m) {
     float s[128];
 #pragma unroll
     for (int i = 0; i < 128; ++i) s[i] = in[i * 128 + threadIdx.x % 128];
@@ -57,7 +58,8 @@ int main() {
             else if (mode == 1) k<1><<<148, warps * 32>>>(in, out, cyc, iters, 0.25f, -1.0f);
             else if (mode == 2) k<2><<<148, warps * 32>>>(in, out, cyc, iters, 0.25f, -1.0f);
             else k<3><<<148, warps * 32>>>(in, out, cyc, iters, 0.25f, -1.0f);
-            cudaError_t e = cudaDeviceSynchronize();
+            cudaError_t e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
             long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
             printf("%-42s %d warp(s) per SMSP: %7.0f cycles per 128-element row per warp  (%s)\n", names[mode], warps / 4, (double)c / iters,
                    cudaGetErrorString(e));
