@@ -148,3 +148,23 @@ def test_run_validation_bookkeeping_cpu(tmp_path):
     y = lambda a: cv2.cvtColor(a, cv2.COLOR_RGB2YCrCb)[:, :, 0]
     assert out["by_sigma"][5]["psnr_y"] == metrics.psnr(y(gt), y(res))
     assert validation.run_validation(0, [], pipe, None, tmp_path) is None
+
+
+def test_gray_prediction_png_comes_back_as_rgb():
+    """cv2.imread(IMREAD_COLOR) replicates a single-channel PNG to three channels; the memory path must do the same."""
+    g = _img(4)["input"][:, :, 0]
+    out = handoff.roundtrip_prediction(Image.fromarray(g, mode="L"), "x.png")
+    assert out.shape == g.shape + (3,) and all(np.array_equal(out[:, :, c], g) for c in range(3))
+
+
+def test_gpu_metric_backend_has_no_silent_fallback():
+    """Asking for the GPU metric pass on a machine without CUDA (this test runs on CPU) must raise, not quietly use numpy."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    calc = metrics.MetricsCalculator(use_lpips=False, device="cuda")
+    a = _img(5)
+    with pytest.raises(Exception):
+        calc.calculate_all(a["input"], a["gt"])
+    with pytest.raises(ValueError):
+        metrics.psnr_ssim_device(torch.zeros((1, 8, 8, 3), dtype=torch.uint8), torch.zeros((1, 8, 8, 3), dtype=torch.uint8))
