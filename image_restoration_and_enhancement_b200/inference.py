@@ -396,6 +396,15 @@ class RestorationPipeline:
                 for i, r in zip(todo, res):
                     out[i] = r
             return out
-        ms = [self._normalize_mask(m if m is not None else self._auto_mask_from_image(im), im.size)
-              for im, m in zip(images, masks or [None] * len(images))]
-        return self._sd_call(task, model, [im.convert("RGB") for im in images], kwargs.get("inpaint_prompt"), mask=ms)
+        # auto-masks first: an image without significant damage is returned unchanged (reference ``:728-731``), the
+        # rest go through one batched call
+        raw = [m if m is not None else self._auto_mask_from_image(im)
+               for im, m in zip(images, masks or [None] * len(images))]
+        todo = [i for i, m in enumerate(raw) if m is not None]
+        out = list(images)
+        if todo:
+            ms = [self._normalize_mask(raw[i], images[i].size) for i in todo]
+            res = self._sd_call(task, model, [images[i].convert("RGB") for i in todo], kwargs.get("inpaint_prompt"), mask=ms)
+            for i, r in zip(todo, res):
+                out[i] = r
+        return out

@@ -72,6 +72,26 @@ def ssim(gt: np.ndarray, pred: np.ndarray, data_range: float = 255.0, channel_ax
     return float(vals.mean())
 
 
+_XYZ_FROM_RGB = np.array([[0.412453, 0.357580, 0.180423], [0.212671, 0.715160, 0.072169],
+                          [0.019334, 0.119193, 0.950227]])
+_D65_WHITE = np.array([0.95047, 1.0, 1.08883])
+
+
+def rgb2lab(rgb: np.ndarray) -> np.ndarray:
+    """skimage.color.rgb2lab (illuminant D65, observer 2) for float RGB in [0, 1]; keeps the input's float dtype."""
+    arr = np.array(rgb, dtype=rgb.dtype if rgb.dtype in (np.float32, np.float64) else np.float64, copy=True)
+    m = arr > 0.04045
+    arr[m] = np.power((arr[m] + 0.055) / 1.055, 2.4)
+    arr[~m] /= 12.92
+    xyz = arr @ _XYZ_FROM_RGB.T.astype(arr.dtype)
+    xyz = xyz / _D65_WHITE.astype(arr.dtype)
+    m = xyz > 0.008856
+    xyz[m] = np.cbrt(xyz[m])
+    xyz[~m] = 7.787 * xyz[~m] + 16.0 / 116.0
+    x, y, z = xyz[..., 0], xyz[..., 1], xyz[..., 2]
+    return np.stack([116.0 * y - 16.0, 500.0 * (x - y), 200.0 * (y - z)], axis=-1)
+
+
 def psnr_ssim_device(pred, gt, data_range: float = 255.0, K1: float = 0.01, K2: float = 0.03):
     """PSNR and SSIM of u8 image batches resident on the GPU: ``pred``, ``gt`` torch.uint8 CUDA tensors [N,H,W,C].
     Returns two lists of Python floats, bit-identical to ``psnr(gt[i], pred[i])`` / ``ssim(gt[i], pred[i])``.
@@ -148,6 +168,14 @@ class MetricsCalculator:
         if not self.use_lpips:
             return None
         return float(self.lpips_fn(_match_shape(pred, gt), gt))
+
+    def calculate_delta_e(self, pred: np.ndarray, gt: np.ndarray, use_delta_e2000: bool = False) -> float:
+        """Mean Delta-E 76 in CIELAB (reference ``src/metrics.py:113-148``; its ``use_delta_e2000`` branch computes the
+        same Euclidean distance).  ``rgb2lab`` restates skimage.color (sRGB companding, D65 / 2-degree white point) in
+        the float32 arithmetic the reference feeds it."""
+        pred = _match_shape(pred, gt)
+        d = rgb2lab(pred.astype(np.float32) / 255.0) - rgb2lab(gt.astype(np.float32) / 255.0)
+        return float(np.mean(np.sqrt(np.sum(d ** 2, axis=2))))
 
     def calculate_all(self, pred: np.ndarray, gt: np.ndarray) -> dict:
         if self._gpu:
@@ -231,3 +259,18 @@ def evaluate_task(pred_dir: Path, gt_dir: Path, task_name: str = "denoise", use_
             if v is not None:
                 per_image.setdefault(k, []).append(v)
     return summarize(task_name, per_image, len(pairs))
+
+
+def print_results(results: dict) -> None:
+    """Pretty print evaluation results (reference ``src/metrics.py:351-365``)."""
+    print(f"\n{'=' * 60}")
+    print(f"Evaluation Results: {results['task']}")
+    print(f"{'=' * 60}")
+    print(f"Number of samples: {results['num_samples']}")
+    print("\nMetrics:")
+    for metric_name, stats in results["metrics"].items():
+        print(f"\n  {metric_name.upper()}:")
+        print(f"    Mean:   {stats['mean']:.4f} \u00b1 {stats['std']:.4f}")
+        print(f"    Median: {stats['median']:.4f}")
+        print(f"    Range:  [{stats['min']:.4f}, {stats['max']:.4f}]")
+    print(f"\n{'=' * 60}\n")

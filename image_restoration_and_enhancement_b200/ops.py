@@ -42,13 +42,23 @@ def _prof_end(e0, work, kind, desc=""):
 
 
 _GN_WS: dict = {}
+GN_WS_MAX_IMAGES = 64     # images per GroupNorm call served by the shared workspace (UNet batch 64 = 32 images under CFG)
 
 
-def _gn_workspace(device, n_floats: int) -> torch.Tensor:
+def _gn_workspace(device, N: int, groups: int) -> torch.Tensor:
+    """One zero-initialised workspace per device, allocated ONCE at its maximum size and never replaced: captured CUDA
+    graphs keep its address, and the self-resetting arrival counters at its head stay valid.  Larger batches get a
+    private zeroed workspace per call (not graph-persistent, so they are refused while a graph is being captured)."""
+    need = GN_MAX_IMAGES + N * groups * 2 + N * GN_MAX_BLOCKS * groups * 2
+    if N > GN_WS_MAX_IMAGES or groups > 32:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError(f"GroupNorm batch {N} exceeds the graph-persistent workspace ({GN_WS_MAX_IMAGES} images)")
+        return torch.zeros((need,), dtype=f32, device=device)
     key = (device.type, device.index)
     ws = _GN_WS.get(key)
-    if ws is None or ws.numel() < n_floats:
-        ws = _GN_WS[key] = torch.zeros((max(n_floats, 1 << 20),), dtype=f32, device=device)
+    if ws is None:
+        full = GN_MAX_IMAGES + GN_WS_MAX_IMAGES * 32 * 2 + GN_WS_MAX_IMAGES * GN_MAX_BLOCKS * 32 * 2
+        ws = _GN_WS[key] = torch.zeros((full,), dtype=f32, device=device)
     return ws
 
 
@@ -202,7 +212,7 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, grou
         # RG_GN_WORKSPACE_FLOATS: counters | (mean, rstd) | per-block partials.  The arrival counters must be zero on
         # entry and reset themselves, so one zero-initialised workspace per device serves every call of a stream.
         assert N <= GN_MAX_IMAGES
-        sums = _gn_workspace(x1.device, GN_MAX_IMAGES + N * groups * 2 + N * GN_MAX_BLOCKS * groups * 2)
+        sums = _gn_workspace(x1.device, N, groups)
     p = RgGn()
     p.x1, p.C1, p.x2, p.C2 = x1.data_ptr(), C1, _ptr(x2), C2
     p.in_dtype, p.N, p.HW, p.groups, p.eps = _dt(x1), N, H * W, groups, eps

@@ -1,7 +1,7 @@
-"""Per-launch profile of one eager UNet evaluation (batch 16) and of VAE encode / decode (batch 8) on the GPU box,
-plus the phase split of one graph-replayed colorize run.  CUDA-event timed per op (not under a profiler).
+"""Per-launch profile of one eager UNet evaluation (UNet batch 2*B) and of VAE encode / decode (batch B) on the GPU box,
+plus the phase split of one graph-replayed sampling run.  CUDA-event timed per op (not under a profiler).
 
-    python tools/gpu_layer_profile.py [tag]      -> gpurun_out/layers_<tag>.txt / .json
+    python tools/gpu_layer_profile.py [tag] [B]      -> gpurun_out/layers_<tag>.txt / .json   (B=8: colorize, B=1: denoise)
 """
 import collections
 import json
@@ -22,7 +22,7 @@ from image_restoration_and_enhancement_b200 import ops, synth
 from image_restoration_and_enhancement_b200.pipelines import StableDiffusionImg2ImgPipeline
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-B = 8
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 dev = torch.device("cuda", 0)
 pipe = StableDiffusionImg2ImgPipeline.from_random_init(seed=0).to(dev)
 out_lines = []
@@ -81,24 +81,37 @@ with torch.no_grad():
     unet.prepare_context(ctx)
     lat = torch.randn((B, 64, 64, 4), device=dev)
     ts = torch.full((2 * B,), 500.0, device=dev)
-    res["unet"] = profile("UNet evaluation, batch 16 (8 images x CFG)", lambda: unet.forward(lat, ts))
+    res["unet"] = profile(f"UNet evaluation, batch {2 * B} ({B} images x CFG)", lambda: unet.forward(lat, ts))
     img = torch.rand((B, 512, 512, 3), device=dev) * 2 - 1
-    res["vae_enc"] = profile("VAE encode, 8 images", lambda: vae.encode_moments(img))
-    res["vae_dec"] = profile("VAE decode, 8 images", lambda: vae.decode(lat * 0.18215))
+    res["vae_enc"] = profile(f"VAE encode, {B} images", lambda: vae.encode_moments(img))
+    res["vae_dec"] = profile(f"VAE decode, {B} images", lambda: vae.decode(lat * 0.18215))
 
     # whole-op timings (eager back-to-back and graph replay)
     say()
-    say(f"eager UNet eval b16: {timed(lambda: unet.forward(lat, ts)):.3f} ms")
+    say(f"eager UNet eval b{2 * B}: {timed(lambda: unet.forward(lat, ts)):.3f} ms")
     run = pipe._unet_step_fn(lat, 2 * B)
-    say(f"graph UNet eval b16: {timed(lambda: run(500)):.3f} ms")
-    say(f"VAE encode b8: {timed(lambda: vae.encode_moments(img)):.3f} ms")
-    say(f"VAE decode b8: {timed(lambda: vae.decode(lat * 0.18215)):.3f} ms")
-    u8 = torch.from_numpy(synth.batch("colorize", range(B))["input"]).to(dev)
+    say(f"graph UNet eval b{2 * B}: {timed(lambda: run(500)):.3f} ms")
+    say(f"VAE encode b{B}: {timed(lambda: vae.encode_moments(img)):.3f} ms")
+    say(f"VAE decode b{B}: {timed(lambda: vae.decode(lat * 0.18215)):.3f} ms")
+    task = "colorize" if B > 1 else "denoise"
+    u8 = torch.from_numpy(synth.batch(task, range(B))["input"]).to(dev)
     gens = lambda: [torch.Generator(device=dev).manual_seed(42) for _ in range(B)]
-    full = lambda: pipe(prompt="x" if False else "vibrant realistic natural colors, colorful, high quality photo, detailed, full color, rich colors",
-                        image=u8, strength=0.75, num_inference_steps=30, guidance_scale=7.5, generator=gens(),
-                        output_type="u8_device")
-    say(f"full colorize run b8: {timed(full, 2):.3f} ms")
+    if B > 1:
+        full = lambda: pipe(prompt="vibrant realistic natural colors, colorful, high quality photo, detailed, full color, rich colors",
+                            image=u8, strength=0.75, num_inference_steps=30, guidance_scale=7.5, generator=gens(),
+                            output_type="u8_device")
+    else:
+        full = lambda: pipe(prompt="clean high quality photo, no noise, sharp details", image=u8, strength=0.5,
+                            num_inference_steps=20, guidance_scale=5.0, generator=gens(), output_type="u8_device")
+    say(f"full {task} run b{B}: {timed(full, 3):.3f} ms")
+    # host-side view of the same run: wall clock per call incl. Python / ctypes / tensor-map encodes of the eager VAE
+    import time
+    torch.cuda.synchronize(); t0 = time.time()
+    for _ in range(3):
+        full()
+    t_issue = (time.time() - t0) / 3
+    torch.cuda.synchronize()
+    say(f"full {task} run b{B}: host issue time {t_issue * 1e3:.3f} ms per call (before the final sync)")
 
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
 (ROOT / "gpurun_out" / f"layers_{tag}.txt").write_text("\n".join(out_lines) + "\n")
