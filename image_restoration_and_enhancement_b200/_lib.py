@@ -11,7 +11,7 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "librestoragen.so"
 
-RG_ACT_NONE, RG_ACT_SILU, RG_ACT_GEGLU = 0, 1, 2
+RG_ACT_NONE, RG_ACT_SILU, RG_ACT_GEGLU, RG_ACT_RELU = 0, 1, 2, 3
 RG_DT_BF16, RG_DT_F32, RG_DT_F16 = 0, 1, 2
 
 
@@ -27,7 +27,8 @@ class RgConv(C.Structure):
                 ("bias", C.c_void_p), ("bias_n", C.c_void_p), ("bias_n_ld", C.c_int64), ("res", C.c_void_p), ("res_dtype", C.c_int32),
                 ("out_bf16", C.c_void_p), ("out_f32", C.c_void_p),
                 ("out_stride_n", C.c_int64), ("out_stride_h", C.c_int64), ("out_stride_w", C.c_int64),
-                ("act", C.c_int32), ("scale", C.c_float), ("out16_dtype", C.c_int32)]
+                ("act", C.c_int32), ("scale", C.c_float), ("out16_dtype", C.c_int32),
+                ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64)]
 
 
 class RgAttn(C.Structure):
@@ -61,6 +62,7 @@ SIGNATURES = {
     "rg_version": (C.c_int, []),
     "rg_launch_count": (C.c_int64, []),
     "rg_device_sm_count": (C.c_int, []),
+    "rg_set_pdl": (C.c_int, [C.c_int]),
     "rg_conv2d": (C.c_int, [C.POINTER(RgConv), _p]),
     "rg_attention": (C.c_int, [C.POINTER(RgAttn), _p]),
     "rg_softmax_rows": (C.c_int, [_p, _i64, _i32, _i64, _p]),
@@ -86,6 +88,9 @@ SIGNATURES = {
     "rg_embed_tokens": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _p, _p]),
     "rg_quick_gelu_bf16": (C.c_int, [_p, _i64, _p]),
     "rg_cast_bf16_f32": (C.c_int, [_p, _i64, _p, _p]),
+    "rg_maxpool3x3s2": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
+    "rg_lpips_layer_blocks": (C.c_int, [_i32]),
+    "rg_lpips_layer": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p, _p]),
     "rg_metrics_sse_u8": (C.c_int, [_p, _p, _i32, _i64, _p, _p]),
     "rg_metrics_ssim_chunks": (C.c_int, [_i32, _i32]),
     "rg_metrics_ssim_u8": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, C.c_double, C.c_double, C.c_double, _p, _p, _p]),

@@ -13,7 +13,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "librestoragen.so"
 STAMP = HERE / "build" / "stamp.txt"
-SOURCES = ["api.cu", "gemm.cu", "attention.cu", "norm.cu", "elementwise.cu", "metrics.cu"]
+SOURCES = ["api.cu", "gemm.cu", "attention.cu", "norm.cu", "elementwise.cu", "metrics.cu", "lpips.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("RG_NVCC_EXTRA", "").split()
 

@@ -23,15 +23,37 @@ int check_launch(const char* kernel) {
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+static std::atomic<int> g_pdl{3};         // bit 0: GEMM / attention / glue kernels, bit 1: norm kernels
+bool pdl_enabled(int cls) { return (g_pdl.load(std::memory_order_relaxed) >> cls) & 1; }
+
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev < 0 ? 0 : (dev >= kMaxDevices ? kMaxDevices - 1 : dev);
+}
+
+// per device: a process may drive several GPUs (one pipeline each)
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static std::atomic<int> n[kMaxDevices];
+    const int dev = current_device();
+    int v = n[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (v <= 0) v = 148;
+        n[dev].store(v, std::memory_order_relaxed);
     }
-    return n;
+    return v;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device AND per function: `done` is the caller's
+// function-local flag array (zero-initialised static), indexed by device
+int ensure_smem_attr(const void* func, int bytes, std::atomic<bool>* done, const char* what) {
+    const int dev = current_device();
+    if (done[dev].load(std::memory_order_acquire)) return RG_OK;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return set_cuda_error(e, what);
+    done[dev].store(true, std::memory_order_release);
+    return RG_OK;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -79,3 +101,4 @@ extern "C" const char* rg_last_error(void) { return rg::g_err; }
 extern "C" int rg_version(void) { return 100; }
 extern "C" int64_t rg_launch_count(void) { return rg::g_launches.load(); }
 extern "C" int rg_device_sm_count(void) { return rg::sm_count(); }
+extern "C" int rg_set_pdl(int mode) { return rg::g_pdl.exchange(mode & 3); }

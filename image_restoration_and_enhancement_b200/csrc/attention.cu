@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kv = (p.Nk + BKV - 1) / BKV;
 
+    pdl_trigger();
     if (warp == 8 && lane == 0) { tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap); }
     if (warp == 9 && lane == 0) {
         mbar_init(&q_full, 1); mbar_init(&q_empty, 1);
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();                         // prologue above overlapped the previous kernel
 
     if (warp == 8) {
         // ===================================================================== TMA producer
@@ -436,13 +438,9 @@ static int encode_qkv_map(CUtensorMap* m, const void* base, int d, int heads, lo
 template <int DKA, int DQK, int DV, int BKV, int SBUF, bool PSEP, int STAGES, bool F16, bool CAUSAL = false>
 static int launch_attn(const rg_attn_t* a, cudaStream_t stream) {
     using Cfg = AttnCfg<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(attention_kernel<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16, CAUSAL>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attention_kernel)");
-        attr_done = true;
-    }
+    static std::atomic<bool> attr_done[kMaxDevices];
+    if (int rc0 = ensure_smem_attr(reinterpret_cast<const void*>(&attention_kernel<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16, CAUSAL>),
+                                   Cfg::SMEM_BYTES, attr_done, "cudaFuncSetAttribute(attention_kernel)")) return rc0;
     AttnParams p;
     memset(&p, 0, sizeof(p));
     int rc;
@@ -460,7 +458,7 @@ static int launch_attn(const rg_attn_t* a, cudaStream_t stream) {
     p.scale_log2 = a->scale * 1.4426950408889634f;
     p.trace = g_attn_trace;
     const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
-    attention_kernel<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16, CAUSAL><<<grid, kAttnThreads, Cfg::SMEM_BYTES, stream>>>(p);
+    launch_kernel(attention_kernel<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16, CAUSAL>, dim3(grid), dim3(kAttnThreads), Cfg::SMEM_BYTES, stream, p);
     count_launch();
     return check_launch("attention_kernel");
 }

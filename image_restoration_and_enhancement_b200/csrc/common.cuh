@@ -15,6 +15,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// ------------------------------------------------------------------------------------ programmatic dependent launch
+// Every hot kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization (internal.h: launch_kernel):
+// pdl_trigger() at the top lets the NEXT kernel of the stream / graph be scheduled while this one runs (its launch
+// latency, barrier init, TMEM allocation and descriptor prefetch overlap this kernel's execution on free SMs and its
+// tail), and pdl_wait() -- executed by every thread before its first access to global memory -- blocks until the
+// PREVIOUS kernel has completed and flushed.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

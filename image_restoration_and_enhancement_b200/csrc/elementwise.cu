@@ -19,6 +19,8 @@ struct SchedParams {
     float c_sample, c_eps;
 };
 __global__ void __launch_bounds__(256) sched_step_kernel(const SchedParams p) {
+    pdl_trigger();
+    pdl_wait();
     RG_GRID_STRIDE(i, p.n) {
         float e;
         if (p.do_cfg) {
@@ -43,6 +45,8 @@ __global__ void __launch_bounds__(256) sched_step_kernel(const SchedParams p) {
 
 // ---------------------------------------------------------------------------------------------- K10 timestep embedding
 __global__ void timestep_embedding_kernel(const float* t, int B, int dim, __nv_bfloat16* out) {
+    pdl_trigger();
+    pdl_wait();
     const int half = dim / 2;
     RG_GRID_STRIDE(i, (long long)B * dim) {
         const int b = (int)(i / dim), j = (int)(i % dim);
@@ -58,6 +62,8 @@ __global__ void timestep_embedding_kernel(const float* t, int B, int dim, __nv_b
 template <bool IN_F32>
 __global__ void im2col_small_kernel(const void* x_, int N, int n_mod, int H, int W, int Cin, int ks, int stride,
                                     int pad, int OH, int OW, int Kpad, __nv_bfloat16* out) {
+    pdl_trigger();
+    pdl_wait();
     const long long total = (long long)N * OH * OW * Kpad;
     const int K = ks * ks * Cin;
     RG_GRID_STRIDE(i, total) {
@@ -82,6 +88,8 @@ __global__ void im2col_small_kernel(const void* x_, int N, int n_mod, int H, int
 // ---------------------------------------------------------------------------------------------- nearest 2x upsample (bf16, 16-B vectors)
 // F.interpolate(mode="nearest"): src = min(floor(dst * in / out), in - 1)
 __global__ void upsample_nearest_kernel(const uint4* x, int N, int H, int W, int C8, int OH, int OW, uint4* y) {
+    pdl_trigger();
+    pdl_wait();
     const long long total = (long long)N * OH * OW * C8;
     const float sh = (float)H / (float)OH, sw = (float)W / (float)OW;
     RG_GRID_STRIDE(i, total) {
@@ -95,6 +103,8 @@ __global__ void upsample_nearest_kernel(const uint4* x, int N, int H, int W, int
 
 // ---------------------------------------------------------------------------------------------- layout
 __global__ void nchw_to_nhwc_kernel(const float* x, int N, int C, int H, int W, float* y) {
+    pdl_trigger();
+    pdl_wait();
     const long long total = (long long)N * C * H * W;
     RG_GRID_STRIDE(i, total) {   // i indexes the NHWC output
         const int c = (int)(i % C); long long r = i / C;
@@ -104,6 +114,8 @@ __global__ void nchw_to_nhwc_kernel(const float* x, int N, int C, int H, int W, 
     }
 }
 __global__ void nhwc_to_nchw_kernel(const float* x, int N, int C, int H, int W, float* y) {
+    pdl_trigger();
+    pdl_wait();
     const long long total = (long long)N * C * H * W;
     RG_GRID_STRIDE(i, total) {   // i indexes the NCHW output
         const int w = (int)(i % W); long long r = i / W;
@@ -114,6 +126,8 @@ __global__ void nhwc_to_nchw_kernel(const float* x, int N, int C, int H, int W, 
 }
 
 __global__ void preprocess_u8_kernel(const uint8_t* img, const float* mask, long long npix, float* out) {
+    pdl_trigger();
+    pdl_wait();
     RG_GRID_STRIDE(i, npix) {
         const float keep = mask ? (mask[i] < 0.5f ? 1.f : 0.f) : 1.f;
 #pragma unroll
@@ -125,6 +139,8 @@ __global__ void preprocess_u8_kernel(const uint8_t* img, const float* mask, long
     }
 }
 __global__ void postprocess_u8_kernel(const float* x, long long npix, int ldc, uint8_t* out) {
+    pdl_trigger();
+    pdl_wait();
     RG_GRID_STRIDE(i, npix) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -137,6 +153,8 @@ __global__ void postprocess_u8_kernel(const float* x, long long npix, int ldc, u
 
 __global__ void vae_sample_kernel(const float* mom, long long ld, const float* eps_post, const float* noise,
                                   long long npix, float scaling, int add_noise, float sa, float sb, float* out) {
+    pdl_trigger();
+    pdl_wait();
     RG_GRID_STRIDE(i, npix * 4) {
         const long long pix = i >> 2; const int c = (int)(i & 3);
         const float mean = mom[pix * ld + c];
@@ -149,6 +167,8 @@ __global__ void vae_sample_kernel(const float* mom, long long ld, const float* e
 
 __global__ void pack_unet_input_kernel(const float* lat, const float* mask, const float* masked, long long npix,
                                        float* out) {
+    pdl_trigger();
+    pdl_wait();
     RG_GRID_STRIDE(i, npix * 9) {
         const long long pix = i / 9; const int c = (int)(i % 9);
         out[i] = c < 4 ? lat[pix * 4 + c] : (c == 4 ? mask[pix] : masked[pix * 4 + c - 5]);
@@ -156,6 +176,8 @@ __global__ void pack_unet_input_kernel(const float* lat, const float* mask, cons
 }
 
 __global__ void mask_nearest_kernel(const float* m, int N, int H, int W, int h, int w, float* out) {
+    pdl_trigger();
+    pdl_wait();
     RG_GRID_STRIDE(i, (long long)N * h * w) {
         const int x = (int)(i % w); long long r = i / w;
         const int y = (int)(r % h); const int n = (int)(r / h);
@@ -167,6 +189,8 @@ __global__ void mask_nearest_kernel(const float* m, int N, int H, int W, int h, 
 
 __global__ void pointwise_small_kernel(const float* x, long long npix, int Cin, int Cout, const float* W,
                                        const float* b, float scale_in, float* out) {
+    pdl_trigger();
+    pdl_wait();
     RG_GRID_STRIDE(i, npix * Cout) {
         const long long pix = i / Cout; const int co = (int)(i % Cout);
         float acc = b ? b[co] : 0.f;
@@ -176,9 +200,13 @@ __global__ void pointwise_small_kernel(const float* x, long long npix, int Cin, 
 }
 
 __global__ void scale_f32_kernel(const float* x, float a, long long n, float* y) {
+    pdl_trigger();
+    pdl_wait();
     RG_GRID_STRIDE(i, n) y[i] = x[i] * a;
 }
 __global__ void cast_f32_bf16_kernel(const float* x, long long n, __nv_bfloat16* y) {
+    pdl_trigger();
+    pdl_wait();
     RG_GRID_STRIDE(i, n) y[i] = __float2bfloat16(x[i]);
 }
 
@@ -191,6 +219,8 @@ namespace rg {
 // CLIPTextEmbeddings: out[b*T + t][:] = token_embedding[ids[b*T + t]][:] + position_embedding[t][:]  (fp32, 4 per thread)
 __global__ void embed_tokens_kernel(const int32_t* ids, const float4* tok, const float4* pos, int rows, int T, int C4,
                                     int vocab, float4* out) {
+    pdl_trigger();
+    pdl_wait();
     RG_GRID_STRIDE(i, (long long)rows * C4) {
         const int r = (int)(i / C4), c = (int)(i % C4);
         int id = ids[r];
@@ -200,10 +230,14 @@ __global__ void embed_tokens_kernel(const int32_t* ids, const float4* tok, const
     }
 }
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* x, long long n, float* y) {
+    pdl_trigger();
+    pdl_wait();
     RG_GRID_STRIDE(i, n) y[i] = __bfloat162float(x[i]);
 }
 // quick_gelu(x) = x * sigmoid(1.702 x), bf16 in place (CLIP MLP activation)
 __global__ void quick_gelu_bf16_kernel(__nv_bfloat162* x, long long n2) {
+    pdl_trigger();
+    pdl_wait();
     RG_GRID_STRIDE(i, n2) {
         const float2 v = __bfloat1622float2(x[i]);
         x[i] = __floats2bfloat162_rn(v.x / (1.f + __expf(-1.702f * v.x)), v.y / (1.f + __expf(-1.702f * v.y)));
@@ -226,14 +260,14 @@ extern "C" int rg_sched_step(const rg_sched_t* s, rg_stream_t stream) {
         p.w4 += *ws[s->store_slot];
         *ws[s->store_slot] = 0.f;
     }
-    sched_step_kernel<<<grid_for(s->n, 256), 256, 0, RG_STREAM(stream)>>>(p);
+    launch_kernel(sched_step_kernel, dim3(grid_for(s->n, 256)), dim3(256), 0, RG_STREAM(stream), p);
     count_launch();
     return check_launch("sched_step_kernel");
 }
 
 extern "C" int rg_timestep_embedding(const float* t, int32_t B, int32_t dim, void* out, rg_stream_t stream) {
     if (!t || !out || dim % 2) return set_error(RG_ERR_ARG, "timestep_embedding: bad argument");
-    timestep_embedding_kernel<<<grid_for((long long)B * dim, 256), 256, 0, RG_STREAM(stream)>>>(
+    launch_kernel(timestep_embedding_kernel, dim3(grid_for((long long)B * dim, 256)), dim3(256), 0, RG_STREAM(stream), 
         t, B, dim, reinterpret_cast<__nv_bfloat16*>(out));
     count_launch();
     return check_launch("timestep_embedding_kernel");
@@ -246,10 +280,10 @@ extern "C" int rg_im2col_small(const void* x, int32_t in_dtype, int32_t N, int32
     const long long total = (long long)N * OH * OW * Kpad;
     auto* o = reinterpret_cast<__nv_bfloat16*>(out);
     if (in_dtype == RG_DT_F32)
-        im2col_small_kernel<true><<<grid_for(total, 256), 256, 0, RG_STREAM(stream)>>>(x, N, n_mod, H, W, Cin, ksize,
+        launch_kernel(im2col_small_kernel<true>, dim3(grid_for(total, 256)), dim3(256), 0, RG_STREAM(stream), x, N, n_mod, H, W, Cin, ksize,
                                                                                       stride, pad, OH, OW, Kpad, o);
     else
-        im2col_small_kernel<false><<<grid_for(total, 256), 256, 0, RG_STREAM(stream)>>>(x, N, n_mod, H, W, Cin, ksize,
+        launch_kernel(im2col_small_kernel<false>, dim3(grid_for(total, 256)), dim3(256), 0, RG_STREAM(stream), x, N, n_mod, H, W, Cin, ksize,
                                                                                        stride, pad, OH, OW, Kpad, o);
     count_launch();
     return check_launch("im2col_small_kernel");
@@ -259,7 +293,7 @@ extern "C" int rg_upsample_nearest(const void* x, int32_t N, int32_t H, int32_t 
                                    void* y, rg_stream_t stream) {
     if (!x || !y || C % 8 || OH < 1 || OW < 1) return set_error(RG_ERR_ARG, "upsample_nearest: bad argument");
     const long long total = (long long)N * OH * OW * (C / 8);
-    upsample_nearest_kernel<<<grid_for(total, 256), 256, 0, RG_STREAM(stream)>>>(
+    launch_kernel(upsample_nearest_kernel, dim3(grid_for(total, 256)), dim3(256), 0, RG_STREAM(stream), 
         reinterpret_cast<const uint4*>(x), N, H, W, C / 8, OH, OW, reinterpret_cast<uint4*>(y));
     count_launch();
     return check_launch("upsample_nearest_kernel");
@@ -267,13 +301,13 @@ extern "C" int rg_upsample_nearest(const void* x, int32_t N, int32_t H, int32_t 
 
 extern "C" int rg_nchw_to_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, float* y, rg_stream_t stream) {
     if (!x || !y) return set_error(RG_ERR_ARG, "nchw_to_nhwc: null pointer");
-    nchw_to_nhwc_kernel<<<grid_for((long long)N * C * H * W, 256), 256, 0, RG_STREAM(stream)>>>(x, N, C, H, W, y);
+    launch_kernel(nchw_to_nhwc_kernel, dim3(grid_for((long long)N * C * H * W, 256)), dim3(256), 0, RG_STREAM(stream), x, N, C, H, W, y);
     count_launch();
     return check_launch("nchw_to_nhwc_kernel");
 }
 extern "C" int rg_nhwc_to_nchw(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, float* y, rg_stream_t stream) {
     if (!x || !y) return set_error(RG_ERR_ARG, "nhwc_to_nchw: null pointer");
-    nhwc_to_nchw_kernel<<<grid_for((long long)N * C * H * W, 256), 256, 0, RG_STREAM(stream)>>>(x, N, C, H, W, y);
+    launch_kernel(nhwc_to_nchw_kernel, dim3(grid_for((long long)N * C * H * W, 256)), dim3(256), 0, RG_STREAM(stream), x, N, C, H, W, y);
     count_launch();
     return check_launch("nhwc_to_nchw_kernel");
 }
@@ -282,7 +316,7 @@ extern "C" int rg_preprocess_u8(const uint8_t* img, const float* mask, int32_t N
                                 rg_stream_t stream) {
     if (!img || !out) return set_error(RG_ERR_ARG, "preprocess_u8: null pointer");
     const long long npix = (long long)N * H * W;
-    preprocess_u8_kernel<<<grid_for(npix, 256), 256, 0, RG_STREAM(stream)>>>(img, mask, npix, out);
+    launch_kernel(preprocess_u8_kernel, dim3(grid_for(npix, 256)), dim3(256), 0, RG_STREAM(stream), img, mask, npix, out);
     count_launch();
     return check_launch("preprocess_u8_kernel");
 }
@@ -290,7 +324,7 @@ extern "C" int rg_postprocess_u8(const float* x, int32_t N, int32_t H, int32_t W
                                  rg_stream_t stream) {
     if (!x || !out || ldc < 3) return set_error(RG_ERR_ARG, "postprocess_u8: bad argument");
     const long long npix = (long long)N * H * W;
-    postprocess_u8_kernel<<<grid_for(npix, 256), 256, 0, RG_STREAM(stream)>>>(x, npix, ldc, out);
+    launch_kernel(postprocess_u8_kernel, dim3(grid_for(npix, 256)), dim3(256), 0, RG_STREAM(stream), x, npix, ldc, out);
     count_launch();
     return check_launch("postprocess_u8_kernel");
 }
@@ -299,7 +333,7 @@ extern "C" int rg_vae_sample(const float* moments, int64_t moments_ld, const flo
                              int64_t npix, float scaling, int32_t add_noise, float sqrt_ac, float sqrt_1mac,
                              float* out, rg_stream_t stream) {
     if (!moments || !eps_post || !out || (add_noise && !noise)) return set_error(RG_ERR_ARG, "vae_sample: null pointer");
-    vae_sample_kernel<<<grid_for(npix * 4, 256), 256, 0, RG_STREAM(stream)>>>(moments, moments_ld, eps_post, noise, npix,
+    launch_kernel(vae_sample_kernel, dim3(grid_for(npix * 4, 256)), dim3(256), 0, RG_STREAM(stream), moments, moments_ld, eps_post, noise, npix,
                                                                               scaling, add_noise, sqrt_ac, sqrt_1mac, out);
     count_launch();
     return check_launch("vae_sample_kernel");
@@ -308,7 +342,7 @@ extern "C" int rg_vae_sample(const float* moments, int64_t moments_ld, const flo
 extern "C" int rg_pack_unet_input(const float* latents, const float* mask, const float* masked, int64_t npix,
                                   float* out, rg_stream_t stream) {
     if (!latents || !mask || !masked || !out) return set_error(RG_ERR_ARG, "pack_unet_input: null pointer");
-    pack_unet_input_kernel<<<grid_for(npix * 9, 256), 256, 0, RG_STREAM(stream)>>>(latents, mask, masked, npix, out);
+    launch_kernel(pack_unet_input_kernel, dim3(grid_for(npix * 9, 256)), dim3(256), 0, RG_STREAM(stream), latents, mask, masked, npix, out);
     count_launch();
     return check_launch("pack_unet_input_kernel");
 }
@@ -316,7 +350,7 @@ extern "C" int rg_pack_unet_input(const float* latents, const float* mask, const
 extern "C" int rg_mask_nearest(const float* mask, int32_t N, int32_t H, int32_t W, int32_t h, int32_t w, float* out,
                                rg_stream_t stream) {
     if (!mask || !out) return set_error(RG_ERR_ARG, "mask_nearest: null pointer");
-    mask_nearest_kernel<<<grid_for((long long)N * h * w, 256), 256, 0, RG_STREAM(stream)>>>(mask, N, H, W, h, w, out);
+    launch_kernel(mask_nearest_kernel, dim3(grid_for((long long)N * h * w, 256)), dim3(256), 0, RG_STREAM(stream), mask, N, H, W, h, w, out);
     count_launch();
     return check_launch("mask_nearest_kernel");
 }
@@ -324,20 +358,20 @@ extern "C" int rg_mask_nearest(const float* mask, int32_t N, int32_t H, int32_t 
 extern "C" int rg_pointwise_small(const float* x, int64_t npix, int32_t Cin, int32_t Cout, const float* W,
                                   const float* b, float scale_in, float* out, rg_stream_t stream) {
     if (!x || !W || !out || Cin > 64 || Cout > 64) return set_error(RG_ERR_ARG, "pointwise_small: bad argument");
-    pointwise_small_kernel<<<grid_for(npix * Cout, 256), 256, 0, RG_STREAM(stream)>>>(x, npix, Cin, Cout, W, b, scale_in, out);
+    launch_kernel(pointwise_small_kernel, dim3(grid_for(npix * Cout, 256)), dim3(256), 0, RG_STREAM(stream), x, npix, Cin, Cout, W, b, scale_in, out);
     count_launch();
     return check_launch("pointwise_small_kernel");
 }
 
 extern "C" int rg_scale_f32(const float* x, float a, int64_t n, float* y, rg_stream_t stream) {
     if (!x || !y) return set_error(RG_ERR_ARG, "scale_f32: null pointer");
-    scale_f32_kernel<<<grid_for(n, 256), 256, 0, RG_STREAM(stream)>>>(x, a, n, y);
+    launch_kernel(scale_f32_kernel, dim3(grid_for(n, 256)), dim3(256), 0, RG_STREAM(stream), x, a, n, y);
     count_launch();
     return check_launch("scale_f32_kernel");
 }
 extern "C" int rg_cast_f32_bf16(const float* x, int64_t n, void* y, rg_stream_t stream) {
     if (!x || !y) return set_error(RG_ERR_ARG, "cast_f32_bf16: null pointer");
-    cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, RG_STREAM(stream)>>>(x, n, reinterpret_cast<__nv_bfloat16*>(y));
+    launch_kernel(cast_f32_bf16_kernel, dim3(grid_for(n, 256)), dim3(256), 0, RG_STREAM(stream), x, n, reinterpret_cast<__nv_bfloat16*>(y));
     count_launch();
     return check_launch("cast_f32_bf16_kernel");
 }
@@ -352,7 +386,7 @@ extern "C" int rg_embed_tokens(const int32_t* ids, const float* token_embedding,
                                int32_t B, int32_t T, int32_t C, int32_t vocab, float* out, rg_stream_t stream) {
     if (!ids || !token_embedding || !position_embedding || !out || B < 1 || T < 1 || C < 4 || C % 4 || vocab < 1)
         return set_error(RG_ERR_ARG, "embed_tokens: bad argument");
-    embed_tokens_kernel<<<grid_for((long long)B * T * (C / 4), 256), 256, 0, RG_STREAM(stream)>>>(
+    launch_kernel(embed_tokens_kernel, dim3(grid_for((long long)B * T * (C / 4), 256)), dim3(256), 0, RG_STREAM(stream), 
         ids, reinterpret_cast<const float4*>(token_embedding), reinterpret_cast<const float4*>(position_embedding), B * T, T,
         C / 4, vocab, reinterpret_cast<float4*>(out));
     count_launch();
@@ -361,13 +395,13 @@ extern "C" int rg_embed_tokens(const int32_t* ids, const float* token_embedding,
 extern "C" int rg_quick_gelu_bf16(void* x, int64_t n, rg_stream_t stream) {
     if (!x || n < 0 || n % 2) return set_error(RG_ERR_ARG, "quick_gelu_bf16: bad argument");
     if (n == 0) return RG_OK;
-    quick_gelu_bf16_kernel<<<grid_for(n / 2, 256), 256, 0, RG_STREAM(stream)>>>(reinterpret_cast<__nv_bfloat162*>(x), n / 2);
+    launch_kernel(quick_gelu_bf16_kernel, dim3(grid_for(n / 2, 256)), dim3(256), 0, RG_STREAM(stream), reinterpret_cast<__nv_bfloat162*>(x), n / 2);
     count_launch();
     return check_launch("quick_gelu_bf16_kernel");
 }
 extern "C" int rg_cast_bf16_f32(const void* x, int64_t n, float* y, rg_stream_t stream) {
     if (!x || !y) return set_error(RG_ERR_ARG, "cast_bf16_f32: null pointer");
-    cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, RG_STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, y);
+    launch_kernel(cast_bf16_f32_kernel, dim3(grid_for(n, 256)), dim3(256), 0, RG_STREAM(stream), reinterpret_cast<const __nv_bfloat16*>(x), n, y);
     count_launch();
     return check_launch("cast_bf16_f32_kernel");
 }

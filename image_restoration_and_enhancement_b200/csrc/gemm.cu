@@ -23,8 +23,9 @@
 //   residual, SiLU / GEGLU), TMA store of the fp32 and / or bf16 box; unit code specialised per epilogue mode at
 //   compile time.  Outputs TMA cannot address (Cout = 3 fp32, unaligned pitches) take the direct epilogue: TMEM ->
 //   registers -> per-warp shared-memory transpose -> row-contiguous global accesses.
-// * Few-pixel levels with a long K (8x8 and below) run split-K x2: both halves are reduce-added by TMA into the
-//   zeroed fp32 output (x + y is commutative: bitwise reproducible), decided per image so results stay batch-invariant.
+// * Few-pixel levels with a long K (32x32 and below) run deterministic split-K (x2 / x4 / x8 by per-image geometry, so
+//   results stay batch-invariant): every K slice dumps its fp32 partial tile into a workspace, the last slice to arrive
+//   (per-warp arrival counters) adds the partials in slice order and runs the normal epilogue (epilogue_splitk).
 // What bounds it (measured): all traffic through L2 -- operand fetches AND epilogue boxes --
 // shares about 6300 B/clk chip-wide; the short-K GEMMs of the transformer blocks sit on that limit, not on the MMA.
 #include <stdlib.h>
@@ -61,7 +62,9 @@ struct GemmParams {
     int prim_f32;                     // dtype of the primary staging buffer (residual in / same-dtype output in place)
     int prim_store;                   // an output of the primary dtype exists
     int sec_store;                    // bf16 output next to an fp32 primary buffer
-    int ksplit, kper;                 // split-K: each tile covers k-blocks [ks*kper, (ks+1)*kper) and is reduce-added
+    int ksplit, kper;                 // split-K: work item (tile, ks) covers k-blocks [ks*kper, (ks+1)*kper)
+    float* ws_part;                   // split-K partial tiles: [out tile][ks][rank][epilogue warp][unit][4][32 lanes] float4
+    int* ws_cnt;                      // split-K arrival counters: [out tile][rank][epilogue warp], zero between launches
     int epi_mode;                     // EPI_* bit set when it matches a specialised epilogue, else EPI_GENERIC
     int dbg;                          // RG_GEMM_DEBUG bits (perf experiments only): 1 skip units, 2 skip stores, 4 skip residual
     int out_f16;                      // the 16-bit output is fp16 (attention operands), not bf16
@@ -102,7 +105,7 @@ struct GemmCfg {
     static_assert(B_CHUNK_BYTES % 1024 == 0, "operand tiles must stay 1024-B aligned");
 };
 
-__device__ __forceinline__ float apply_act(float x, int act) { return act == 1 ? silu_f(x) : x; }
+__device__ __forceinline__ float apply_act(float x, int act) { return act == 1 ? silu_f(x) : (act == 3 ? fmaxf(x, 0.f) : x); }
 
 // geometry of the 128 accumulator rows a CTA owns for one tile
 struct RowGeom {
@@ -137,11 +140,11 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
     constexpr bool G = MODE == EPI_GENERIC;
     const bool geglu = G ? p.act == 2 : (MODE & EPI_GEGLU) != 0;
     const bool silu = G ? p.act == 1 : (MODE & EPI_SILU) != 0;
+    const bool relu = G && p.act == 3;                    // LPIPS feature convs: run-time-flag epilogue only
     const bool prim_f32 = G ? p.prim_f32 != 0 : (MODE & EPI_PRIM_F32) != 0;
     const bool prim_store = G ? p.prim_store != 0 : (MODE & EPI_PRIM_STORE) != 0;
     const bool sec_store = G ? p.sec_store != 0 : (MODE & EPI_SEC_STORE) != 0;
-    // (split-K reads the residual with plain loads in its leading split only: no TMA prefetch chain)
-    const bool has_res = G ? (p.res != nullptr && !(p.dbg & 4) && p.ksplit == 1) : (MODE & EPI_RES) != 0;
+    const bool has_res = G ? (p.res != nullptr && !(p.dbg & 4)) : (MODE & EPI_RES) != 0;
     const bool skip_units = G && (p.dbg & 1) != 0, skip_store = G && (p.dbg & 2) != 0;
     const float scale = (G || (MODE & EPI_SCALE)) ? p.scale : 1.0f;
     const float* const bias = (G || (MODE & EPI_BIAS)) ? p.bias : nullptr;
@@ -156,8 +159,7 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
     uint8_t* const hbuf0 = pbuf0 + NBUF * 2048;
     uint64_t* const res_bar = res_bar_all + ew * NBUF;
     const uint32_t acc_empty_leader = mapa_shared(smem_u32(acc_empty), 0);
-    const int total_tiles = p.n_pairs_m * p.n_tiles_n * p.ksplit;
-    const bool split = G && p.ksplit > 1;                 // split-K tiles are reduce-added into a zeroed fp32 output
+    const int total_tiles = p.n_pairs_m * p.n_tiles_n;   // (split-K launches take epilogue_splitk instead)
     const int TW = 1 << p.lw, TH = 1 << p.lh, lwh = p.lw + p.lh, TN = 128 >> lwh;
     const int row0 = q * 32;
     const int res_bytes = prim_f32 ? 2048 : 1024;
@@ -167,9 +169,8 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
 
     // box origin (w, h, n) of this warp's 32 rows in tile `tile`
     auto box_origin = [&](int tile, int& cw, int& ch, int& cn, int& n_tile, int& tni) {
-        const int t2 = tile / p.ksplit;
-        const int mp = t2 / p.n_tiles_n;
-        n_tile = t2 - mp * p.n_tiles_n;
+        const int mp = tile / p.n_tiles_n;
+        n_tile = tile - mp * p.n_tiles_n;
         const int m_tile = 2 * mp + (int)rank;
         const int twi = m_tile % p.tiles_w;
         const int rest = m_tile / p.tiles_w;
@@ -195,18 +196,8 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
         if (has_next) box_origin(tile + n_clusters, cw2, ch2, cn2, n_tile2, tni2);
         int n_row = tni * TN + ((row0 + lane) >> lwh);
         if (n_row >= p.N) n_row = p.N - 1;                // padding rows: any valid image (their result is clipped)
-        const bool lead = !split || (tile % p.ksplit) == 0;      // the split that adds bias / residual
-        const float* const bn_row = (use_bn && lead) ? p.bias_n + (long long)n_row * p.bias_n_ld : nullptr;
-        const float* const bias_t = lead ? bias : nullptr;
-        const float* res_row = nullptr;                    // split-K only: this lane's residual row (fp32), if it is a real pixel
-        if (split && lead && p.res) {
-            const int row = row0 + lane;
-            const int ow = cw - (row0 & (TW - 1)) + (row & (TW - 1));
-            const int oh = ch - ((row0 >> p.lw) & (TH - 1)) + ((row >> p.lw) & (TH - 1));
-            const int n = tni * TN + (row >> lwh);
-            if (ow < p.OW && oh < p.OH && n < p.N)
-                res_row = reinterpret_cast<const float*>(p.res) + (long long)n * p.osn + (long long)oh * p.osh + (long long)ow * p.osw;
-        }
+        const float* const bn_row = use_bn ? p.bias_n + (long long)n_row * p.bias_n_ld : nullptr;
+        const float* const bias_t = bias;
 #pragma unroll 1
         for (int c = 0; c < NC; ++c) {
             const uint32_t slot = (cc + c) % Cfg::SLOTS, use = (cc + c) / Cfg::SLOTS;
@@ -284,10 +275,6 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
                             const float4 b = __ldg(reinterpret_cast<const float4*>(bias_t + gcol + 4 * j));
                             y0 += b.x; y1 += b.y; y2 += b.z; y3 += b.w;
                         }
-                        if (G && res_row) {
-                            const float4 r = *reinterpret_cast<const float4*>(res_row + gcol + 4 * j);
-                            y0 += r.x; y1 += r.y; y2 += r.z; y3 += r.w;
-                        }
                         if (bn_row) {
                             const float4 b = __ldg(reinterpret_cast<const float4*>(bn_row + gcol + 4 * j));
                             y0 += b.x; y1 += b.y; y2 += b.z; y3 += b.w;
@@ -296,6 +283,7 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
                             float4* const slot4 = reinterpret_cast<float4*>(pb + fo + ((j ^ sw) << 4));
                             if (has_res) { const float4 r = *slot4; y0 += r.x; y1 += r.y; y2 += r.z; y3 += r.w; }
                             if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+                            if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
                             if (prim_store) *slot4 = make_float4(y0, y1, y2, y3);
                             if (sec_store) { pk[2 * j] = pack16(y0, y1); pk[2 * j + 1] = pack16(y2, y3); }
                         } else {
@@ -304,6 +292,7 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
                                 y0 += f0.x; y1 += f0.y; y2 += f1.x; y3 += f1.y;
                             }
                             if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+                            if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
                             pk[2 * j] = pack16(y0, y1); pk[2 * j + 1] = pack16(y2, y3);
                         }
                     }
@@ -317,8 +306,7 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0 && !skip_store) {
-                    if (split) tma_reduce_add_4d(&p.pmap, pb, ocol, cw, ch, cn);
-                    else if (prim_store) tma_store_4d(&p.pmap, pb, ocol, cw, ch, cn);
+                    if (prim_store) tma_store_4d(&p.pmap, pb, ocol, cw, ch, cn);
                     if (sec_store) tma_store_4d(&p.hmap, hb, ocol, cw, ch, cn);
                     bulk_commit();
                 }
@@ -330,7 +318,163 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
         }
         cw = cw2; ch = ch2; cn = cn2; n_tile = n_tile2; tni = tni2;
     }
-    if (lane == 0) bulk_wait_all();                       // every store has landed before the CTA may exit
+    if (lane == 0) bulk_wait_read<0>();                   // the stores have read their shared-memory source: the CTA may exit
+    __syncwarp();                                         // (the writes themselves are flushed by the end of the grid)
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Deterministic split-K epilogue (NC = 1, EW = 8).  Work item = (output tile t2, K slice ks), ks fastest, so the slices
+// of one tile run on neighbouring clusters at the same time.  Every epilogue warp owns 32 accumulator rows and its
+// share of the tile's 16-column units, exactly as in epilogue_tma:
+//   phase 1  dump the raw fp32 accumulator units into the workspace region of (t2, ks, rank, warp) -- lane-interleaved
+//            float4s, so every store instruction writes 512 contiguous bytes -- release the TMEM slot, fence, and bump
+//            the arrival counter of (t2, rank, warp);
+//   phase 2  only the warp whose arrival was the last of the ksplit slices: read the partials of ALL slices back
+//            (L2 hits) and add them in slice order 0..ksplit-1 -- the order never depends on who arrived when, so the
+//            result is bitwise reproducible -- then scale / bias / per-image bias / residual / SiLU and the TMA
+//            store(s) of the finished box.  The counter is reset by the warp that consumed it.
+// No CTA ever waits for another one (the last arriver does the work), so there is no forward-progress hazard.
+constexpr int kMaxSplit = 8;
+
+template <int BNC, int EW>
+__device__ __noinline__ void epilogue_splitk(const GemmParams& p, uint8_t* staging, uint64_t* acc_full, uint64_t* acc_empty,
+                                             uint32_t tmem_base, uint32_t rank, int cluster_id, int n_clusters, int warp,
+                                             int lane) {
+    using Cfg = GemmCfg<BNC, 1, EW>;
+    constexpr int NBUF = Cfg::NBUF, HBUF = Cfg::HBUF, PARTS = Cfg::PARTS;
+    static_assert(NBUF >= 2 && HBUF >= 2, "split-K epilogue rotates two store buffers");
+    constexpr int UPC = BNC / 16;                         // 16-column units per tile
+    constexpr int CNT_MAX = (UPC + PARTS - 1) / PARTS;    // units per warp (region pitch)
+    constexpr int REGION = CNT_MAX * 512;                 // floats per (tile, slice, rank, warp)
+    const int ew = warp - 2, q = warp & 3, part = ew >> 2;
+    const int CNT = (UPC - part + PARTS - 1) / PARTS;
+    uint8_t* const pbuf0 = staging + ew * Cfg::WARP_STAGING;
+    uint8_t* const hbuf0 = pbuf0 + NBUF * 2048;
+    const uint32_t acc_empty_leader = mapa_shared(smem_u32(acc_empty), 0);
+    const int total_tiles = p.n_pairs_m * p.n_tiles_n * p.ksplit;
+    const int TW = 1 << p.lw, TH = 1 << p.lh, lwh = p.lw + p.lh, TN = 128 >> lwh;
+    const int row0 = q * 32, row = row0 + lane;
+    const int sw = (lane >> 1) & 3, fo = lane * 64, ho = lane * 32, hsw = (lane >> 2) & 1;
+    const bool prim_f32 = p.prim_f32 != 0, prim_store = p.prim_store != 0, sec_store = p.sec_store != 0;
+    const bool silu = p.act == 1, relu = p.act == 3, out_f16 = p.out_f16 != 0, res_f32 = p.res_f32 != 0;
+    const float scale = p.scale;
+    auto pack16 = [&](float lo, float hi) { return out_f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); };
+    const size_t slice_pitch = (size_t)2 * EW * REGION;   // floats between slice s and s + 1 of one output tile
+    uint32_t cc = 0, A = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++cc) {
+        const int ks = tile % p.ksplit, t2 = tile / p.ksplit;
+        const int mp = t2 / p.n_tiles_n, n_tile = t2 - mp * p.n_tiles_n;
+        const int m_tile = 2 * mp + (int)rank;
+        const int twi = m_tile % p.tiles_w;
+        const int rest = m_tile / p.tiles_w;
+        const int thi = rest % p.tiles_h, tni = rest / p.tiles_h;
+        const int cw = twi * TW + (row0 & (TW - 1)), ch = thi * TH + ((row0 >> p.lw) & (TH - 1)), cn = tni * TN + (row0 >> lwh);
+        const int ow = twi * TW + (row & (TW - 1)), oh = thi * TH + ((row >> p.lw) & (TH - 1)), n = tni * TN + (row >> lwh);
+        const bool valid = ow < p.OW && oh < p.OH && n < p.N;
+        const bool any_valid = __any_sync(0xffffffffu, valid);       // all-padding warps (odd last tile, M < 256) skip the dump
+        const uint32_t slot = cc % Cfg::SLOTS, use = cc / Cfg::SLOTS;
+        mbar_wait(&acc_full[slot], use & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)row0 << 16) + slot * BNC;
+        float* const tile_base = p.ws_part + ((size_t)t2 * p.ksplit * 2 + rank) * EW * REGION + (size_t)ew * REGION;
+        // ---- phase 1: dump this slice's partial units
+        if (any_valid) {
+            float4* const my = reinterpret_cast<float4*>(tile_base + (size_t)ks * slice_pitch);
+#pragma unroll 1
+            for (int k = 0; k < CNT; ++k) {
+                uint32_t va[16];
+                tmem_ld16(taddr + (part + PARTS * k) * 16, va);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    __stcg(my + k * 128 + j * 32 + lane, make_float4(__uint_as_float(va[4 * j]), __uint_as_float(va[4 * j + 1]),
+                                                                      __uint_as_float(va[4 * j + 2]), __uint_as_float(va[4 * j + 3])));
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_leader + slot * 8);
+        if (!any_valid) continue;
+        // ---- publish, elect the last arriver
+        __threadfence();
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+            int* const c = p.ws_cnt + ((size_t)t2 * 2 + rank) * EW + ew;
+            last = atomicAdd(c, 1) == p.ksplit - 1;
+            if (last) atomicExch(c, 0);                    // self-resetting: every slice of this launch has arrived
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) continue;
+        __threadfence();
+        // ---- phase 2: ordered reduction + the normal epilogue
+        const long long off = valid ? (long long)n * p.osn + (long long)oh * p.osh + (long long)ow * p.osw : 0;
+        const float* const bn_row = p.bias_n ? p.bias_n + (long long)(n < p.N ? n : p.N - 1) * p.bias_n_ld : nullptr;
+        const float4* const part0 = reinterpret_cast<const float4*>(tile_base);
+#pragma unroll 1
+        for (int k = 0; k < CNT; ++k, ++A) {
+            const int gcol = n_tile * BNC + (part + PARTS * k) * 16;
+            uint8_t* const pb = pbuf0 + (A % 2) * 2048;
+            uint8_t* const hb = hbuf0 + (A % 2) * 1024;
+            if (lane == 0) bulk_wait_read<1>();            // the store issued two units ago has drained these buffers
+            __syncwarp();
+            // every partial of the unit is requested before the first one is used (32 independent L2 loads per lane in
+            // flight; a serial load -> add chain cost one L2 round trip per slice and column group), then added in slice
+            // order: fixed, independent of arrival order
+            float4 part[kMaxSplit][4];
+#pragma unroll
+            for (int s2 = 0; s2 < kMaxSplit; ++s2)
+                if (s2 < p.ksplit) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) part[s2][j] = __ldcg(part0 + (size_t)s2 * (slice_pitch / 4) + k * 128 + j * 32 + lane);
+                }
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 a = part[0][j];
+#pragma unroll
+                for (int s2 = 1; s2 < kMaxSplit; ++s2)
+                    if (s2 < p.ksplit) { a.x += part[s2][j].x; a.y += part[s2][j].y; a.z += part[s2][j].z; a.w += part[s2][j].w; }
+                float y0 = a.x * scale, y1 = a.y * scale, y2 = a.z * scale, y3 = a.w * scale;
+                if (p.bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol + 4 * j));
+                    y0 += b.x; y1 += b.y; y2 += b.z; y3 += b.w;
+                }
+                if (bn_row) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(bn_row + gcol + 4 * j));
+                    y0 += b.x; y1 += b.y; y2 += b.z; y3 += b.w;
+                }
+                if (p.res && valid) {
+                    if (res_f32) {
+                        const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + off + gcol + 4 * j);
+                        y0 += r.x; y1 += r.y; y2 += r.z; y3 += r.w;
+                    } else {
+                        const uint2 r2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + off + gcol + 4 * j);
+                        const float2 f0 = unpack_bf16x2(r2.x), f1 = unpack_bf16x2(r2.y);
+                        y0 += f0.x; y1 += f0.y; y2 += f1.x; y3 += f1.y;
+                    }
+                }
+                if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+                if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
+                if (prim_f32 && prim_store) *reinterpret_cast<float4*>(pb + fo + ((j ^ sw) << 4)) = make_float4(y0, y1, y2, y3);
+                pk[2 * j] = pack16(y0, y1); pk[2 * j + 1] = pack16(y2, y3);
+            }
+            if (!prim_f32 || sec_store) {
+                uint8_t* const bb = prim_f32 ? hb : pb;
+                *reinterpret_cast<uint4*>(bb + ho + (hsw << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(bb + ho + ((hsw ^ 1) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if (prim_store) tma_store_4d(&p.pmap, pb, gcol, cw, ch, cn);
+                if (sec_store) tma_store_4d(&p.hmap, hb, gcol, cw, ch, cn);
+                bulk_commit();
+            }
+        }
+    }
+    if (lane == 0) bulk_wait_read<0>();
     __syncwarp();
 }
 
@@ -354,6 +498,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
+    pdl_trigger();                      // the next kernel may be scheduled now (it waits for this one before touching memory)
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 5; ++i) tma_prefetch_desc(&p.amap[i]);
         tma_prefetch_desc(&p.bmap);
@@ -370,6 +515,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     cluster_sync_all();                 // barriers of BOTH CTAs are initialised before anyone signals across the pair
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    pdl_wait();                         // everything above overlapped the previous kernel; from here on its results are needed
 
     // work items: (pair of 128-pixel tiles, column tile, K split); the K split is the fastest index
     const int total_tiles = p.n_pairs_m * p.n_tiles_n * p.ksplit;
@@ -450,7 +596,10 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         }
     } else {
         // ===================================================================== epilogue (both CTAs, own 128 rows)
-        if (p.epi_tma) {
+        if (p.ksplit > 1) {
+            if constexpr (NC == 1 && EW == 8)
+                epilogue_splitk<BNC, EW>(p, staging, acc_full, acc_empty, tmem_base, rank, cluster_id, n_clusters, warp, lane);
+        } else if (p.epi_tma) {
 #define RG_EPI_CASE(M) case (M): epilogue_tma<BNC, NC, EW, (M)>(p, staging, acc_full, acc_empty, res_bar, tmem_base, rank, cluster_id, n_clusters, warp, lane); break;
             switch (p.epi_mode) {
                 RG_EPI_CASE(EPI_PRIM_STORE)                                                   // bf16 out
@@ -600,6 +749,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
                                         float y0 = x[i].x * p.scale + b.x + rr[i].x, y1 = x[i].y * p.scale + b.y + rr[i].y;
                                         float y2 = x[i].z * p.scale + b.z + rr[i].z, y3 = x[i].w * p.scale + b.w + rr[i].w;
                                         if (p.act == 1) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+                                        if (p.act == 3) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
                                         if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + g.off[i] + col) = make_float4(y0, y1, y2, y3);
                                         if (p.out_bf16)
                                             *reinterpret_cast<uint2*>(p.out_bf16 + g.off[i] + col) =
@@ -665,13 +815,9 @@ static int encode_act_map(CUtensorMap* m, const void* base, int C, long long W, 
 template <int BNC, int NC, int EW = 8>
 static int launch_gemm(GemmParams& gp, const void* w, long long ktot, long long w_ld, cudaStream_t stream) {
     using Cfg = GemmCfg<BNC, NC, EW>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BNC, NC, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_gemm_kernel)");
-        attr_done = true;
-    }
+    static std::atomic<bool> attr_done[kMaxDevices];
+    if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&conv_gemm_kernel<BNC, NC, EW>), Cfg::SMEM_BYTES, attr_done,
+                                  "cudaFuncSetAttribute(conv_gemm_kernel)")) return rc;
     {
         cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)gp.Cout};
         cuuint64_t strides[1] = {(cuuint64_t)w_ld * 2};
@@ -686,7 +832,7 @@ static int launch_gemm(GemmParams& gp, const void* w, long long ktot, long long 
     const int total = gp.n_pairs_m * gp.n_tiles_n * gp.ksplit;
     const int max_clusters = sm_count() / 2;
     const int clusters = total < max_clusters ? total : max_clusters;
-    conv_gemm_kernel<BNC, NC, EW><<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(gp);
+    launch_kernel(conv_gemm_kernel<BNC, NC, EW>, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, gp);
     count_launch();
     return check_launch("conv_gemm_kernel");
 }
@@ -792,11 +938,13 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
     // ---- TMA epilogue: per-warp boxes of {16 columns, 32 pixels}; needs 16-byte aligned row segments and a residual
     // of the same dtype as the buffer it is combined in (fp32 residual -> fp32 primary buffer, else the output dtype)
     gp.out_cols = c->act == RG_ACT_GEGLU ? c->Cout / 2 : c->Cout;
+#ifdef RG_GEMM_TUNING            /* perf experiments only (RG_NVCC_EXTRA=-DRG_GEMM_TUNING): never in the product build */
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("RG_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
         gp.dbg = dbg;
     }
+#endif
     {
         const bool res_f32 = c->res && c->res_dtype == RG_DT_F32, res_b16 = c->res && c->res_dtype == RG_DT_BF16;
         const bool prim_f32 = c->res ? res_f32 : (c->out_f32 != nullptr);
@@ -839,6 +987,7 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
             if (c->bias) mode |= 32;
             if (c->bias_n) mode |= 64;
             if (c->act == RG_ACT_SILU) mode |= 128;
+            if (c->act == RG_ACT_RELU) mode |= 1 << 20;  // no specialised unit code: run-time-flag epilogue
             if (c->scale != 1.0f) mode |= 256;
             if (c->out16_dtype == RG_DT_F16) mode |= 512;
             gp.epi_mode = gp.dbg ? (1 << 20) : mode;    // debug experiments run the generic (run-time flag) epilogue
@@ -855,28 +1004,45 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
     gp.ksplit = 1;
     gp.kper = gp.total_kblk;
     const int clusters = sm_count() / 2;
-    // ---- split-K (x2) for the few-pixel levels with a long K (8x8 and below in the UNet): both halves are reduce-added
-    // by TMA into the zero-initialised fp32 output; x + y is commutative, so the result does not depend on arrival order.
-    if (gp.epi_tma && Cout % 160 == 0 && gp.prim_f32 && gp.prim_store && !gp.sec_store && c->act == RG_ACT_NONE &&
-        gp.total_kblk >= 32 && OH * OW <= 64 &&          /* decided per image, never by N: results stay batch-invariant */
-        (!c->res || c->res_dtype == RG_DT_F32) && c->res != (const void*)c->out_f32 &&
-        c->out_stride_w == Cout && c->out_stride_h == (long long)OW * Cout && c->out_stride_n == (long long)OH * OW * Cout) {
-        cudaError_t e = cudaMemsetAsync(c->out_f32, 0, (size_t)N * OH * OW * Cout * sizeof(float), stream);
-        if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(split-K output)");
-        gp.ksplit = 2;
-        gp.kper = (gp.total_kblk + 1) / 2;
-        gp.epi_mode = 1 << 20;                           // run-time-flag epilogue
-        return launch_gemm<160, 1>(gp, c->w, ktot, w_ld, stream);
+    // ---- deterministic split-K for the few-pixel levels with a long K (epilogue_splitk).  The slice count is a function
+    // of the PER-IMAGE geometry (OH*OW, K) only -- never of N -- so an image's result does not depend on the batch size.
+    if (gp.epi_tma && Cout % 160 == 0 && c->act != RG_ACT_GEGLU && c->splitk_ws && gp.dbg == 0) {
+        const long long hw = (long long)OH * OW;
+        // at most 8 / 4 / 2 slices at the 8x8 / 16x16 / 32x32 levels, at least 12 k-blocks per slice, and only when the
+        // main loop is long enough (>= 48 k-blocks) to pay for the dump + fix-up (about 3 us, i.e. ~18 k-blocks of MMA)
+        int ks = hw <= 64 ? 8 : hw <= 256 ? 4 : hw <= 1024 ? 2 : 1;
+        if (gp.total_kblk < 48) ks = 1;
+        if (ks > gp.total_kblk / 12) ks = gp.total_kblk / 12;
+        if (ks > 1) {
+            using Cfg = GemmCfg<160, 1, 8>;
+            constexpr long long kRegion = (long long)((Cfg::N_TILE / 16 + Cfg::PARTS - 1) / Cfg::PARTS) * 2048;   // bytes per (tile, slice, rank, warp)
+            const long long out_tiles = (long long)gp.n_pairs_m * (Cout / 160);
+            const long long cnt_bytes = out_tiles * 2 * 8 * (long long)sizeof(int);
+            const long long part_bytes = out_tiles * ks * 2 * 8 * kRegion;
+            if ((reinterpret_cast<uintptr_t>(c->splitk_ws) & 15) == 0 && cnt_bytes <= RG_SPLITK_COUNTER_BYTES &&
+                RG_SPLITK_COUNTER_BYTES + part_bytes <= c->splitk_ws_bytes) {
+                gp.ksplit = ks;
+                gp.kper = (gp.total_kblk + ks - 1) / ks;
+                if ((long long)gp.kper * (ks - 1) >= gp.total_kblk) {               // an empty last slice would never commit
+                    gp.ksplit = 1; gp.kper = gp.total_kblk;
+                } else {
+                    gp.ws_cnt = reinterpret_cast<int*>(c->splitk_ws);
+                    gp.ws_part = reinterpret_cast<float*>(reinterpret_cast<char*>(c->splitk_ws) + RG_SPLITK_COUNTER_BYTES);
+                    return launch_gemm<160, 1>(gp, c->w, ktot, w_ld, stream);
+                }
+            }
+        }
     }
     auto waves = [&](int n_tile) { return (int)(((long long)gp.n_pairs_m * ((Cout + n_tile - 1) / n_tile) + clusters - 1) / clusters); };
     if (Cout % 160 == 0) {
         // short K: the epilogue dominates and wants the full double buffering of the 1 x 160 tile (3 TMEM slots)
-        static int min_kblk = -1;
-        if (min_kblk < 0) { const char* e = getenv("RG_GEMM_NC2_MIN_KBLK"); min_kblk = e ? atoi(e) : 24; }
+        int min_kblk = 24, ew16 = 24;
+#ifdef RG_GEMM_TUNING
+        { const char* e = getenv("RG_GEMM_NC2_MIN_KBLK"); if (e) min_kblk = atoi(e); }
+        { const char* e = getenv("RG_GEMM_EW16_MAX_KBLK"); if (e) ew16 = atoi(e); }
+#endif
         if (Cout % 320 == 0 && gp.total_kblk > min_kblk && (long long)waves(320) * 865 <= (long long)waves(160) * 625)
             return launch_gemm<160, 2>(gp, c->w, ktot, w_ld, stream);
-        static int ew16 = -1;
-        if (ew16 < 0) { const char* e = getenv("RG_GEMM_EW16_MAX_KBLK"); ew16 = e ? atoi(e) : 24; }
         if (gp.epi_tma && gp.total_kblk <= ew16) return launch_gemm<160, 1, 16>(gp, c->w, ktot, w_ld, stream);
         return launch_gemm<160, 1>(gp, c->w, ktot, w_ld, stream);
     }

@@ -16,6 +16,7 @@
 //     leaf, leaves combined by the recursive halving rule), chunk sums added sequentially.  ssim_chunk_sum_kernel
 //     reproduces the leaf / tree structure; the host adds the (few) chunk sums in order and divides.
 // tests/test_kernels_gpu.py checks bit equality against image_restoration_and_enhancement_b200.metrics (numpy/scipy).
+#include "common.cuh"
 #include "internal.h"
 
 namespace rg {
@@ -29,6 +30,8 @@ constexpr int MAX_LEAVES = 256;
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sse_u8_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
                                                      unsigned long long* __restrict__ sse, long long elems) {
+    pdl_trigger();
+    pdl_wait();
     const int n = blockIdx.y;
     const uint8_t* pa = a + (long long)n * elems;
     const uint8_t* pb = b + (long long)n * elems;
@@ -94,6 +97,8 @@ __device__ __forceinline__ Five vertical7(const uint8_t* __restrict__ pa, const 
 __global__ void __launch_bounds__(64) ssim_map_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
                                                       double* __restrict__ smap, int H, int W, int C, double c1,
                                                       double c2, double cov_norm) {
+    pdl_trigger();
+    pdl_wait();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const int HC = H - 2 * SSIM_PAD, WC = W - 2 * SSIM_PAD;
     if (r >= HC) return;
@@ -175,6 +180,8 @@ __device__ double pw_combine(int n, const double* leaf_sum, int& idx) {
 __global__ void __launch_bounds__(256) ssim_chunk_sum_kernel(const double* __restrict__ smap,
                                                              double* __restrict__ chunk_sums, int HC, int WC,
                                                              int rows_per_chunk) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ int leaf_off[MAX_LEAVES], leaf_n[MAX_LEAVES];
     __shared__ double leaf_sum[MAX_LEAVES];
     __shared__ int n_leaves;
@@ -234,7 +241,7 @@ extern "C" int rg_metrics_sse_u8(const uint8_t* pred, const uint8_t* gt, int32_t
     int bx = (int)((elems_per_image + per_block - 1) / per_block);
     if (bx < 1) bx = 1;
     if (bx > 1024) bx = 1024;
-    sse_u8_kernel<<<dim3(bx, N), 256, 0, stream>>>(pred, gt, reinterpret_cast<unsigned long long*>(sse),
+    launch_kernel(sse_u8_kernel, dim3(dim3(bx, N)), dim3(256), 0, stream, pred, gt, reinterpret_cast<unsigned long long*>(sse),
                                                    (long long)elems_per_image);
     count_launch();
     return check_launch("sse_u8_kernel");
@@ -258,11 +265,11 @@ extern "C" int rg_metrics_ssim_u8(const uint8_t* pred, const uint8_t* gt, int32_
     if (chunks < 1) return set_error(RG_ERR_ARG, "rg_metrics_ssim_u8: width - 6 exceeds numpy's 8192-element buffer");
     const int HC = H - 2 * SSIM_PAD, WC = W - 2 * SSIM_PAD;
     // gt is im1 (x), pred is im2 (y): the expression is symmetric operation by operation, the order is kept anyway
-    ssim_map_kernel<<<dim3((HC + 63) / 64, C, N), 64, 0, stream>>>(gt, pred, smap_ws, H, W, C, c1, c2, cov_norm);
+    launch_kernel(ssim_map_kernel, dim3(dim3((HC + 63) / 64, C, N)), dim3(64), 0, stream, gt, pred, smap_ws, H, W, C, c1, c2, cov_norm);
     count_launch();
     int rc = check_launch("ssim_map_kernel");
     if (rc != RG_OK) return rc;
-    ssim_chunk_sum_kernel<<<dim3(chunks, C, N), 256, 0, stream>>>(smap_ws, chunk_sums, HC, WC, NPY_BUFSIZE / WC);
+    launch_kernel(ssim_chunk_sum_kernel, dim3(dim3(chunks, C, N)), dim3(256), 0, stream, smap_ws, chunk_sums, HC, WC, NPY_BUFSIZE / WC);
     count_launch();
     return check_launch("ssim_chunk_sum_kernel");
 }

@@ -94,6 +94,8 @@ __device__ __forceinline__ float* gn_partials(const GnParams& p) { return gn_fin
 // grid = (blocks_per_image, N); block = tpr * rpb threads
 template <bool IN_F32>
 __global__ void __launch_bounds__(512) gn_stats_kernel(const GnParams p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float s_red[];          // [rpb][tpr][16] thread partials, then [C][2] channel sums
     const int n = blockIdx.y;
     const int tc = threadIdx.x % p.tpr, tr = threadIdx.x / p.tpr;
@@ -212,6 +214,8 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const GnParams p) {
 
 template <bool IN_F32>
 __global__ void __launch_bounds__(512, IN_F32 ? 2 : 1) gn_apply_kernel(const GnParams p) {
+    pdl_trigger();
+    pdl_wait();
     const int n = blockIdx.y;
     const int tc = threadIdx.x % p.tpr, tr = threadIdx.x / p.tpr;
     if (tr >= p.rpb) return;
@@ -278,6 +282,8 @@ __global__ void __launch_bounds__(512, IN_F32 ? 2 : 1) gn_apply_kernel(const GnP
 // grid = (groups, N), 256 threads, dynamic smem = HW * cpg * sizeof(input element)
 template <bool IN_F32>
 __global__ void __launch_bounds__(256) gn_fused_small_kernel(const GnParams p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char s_slice[];
     __shared__ double s_part[2][8];
     __shared__ float s_stat[2];
@@ -406,6 +412,8 @@ template <bool IN_F32, int EPL>
 __global__ void __launch_bounds__(256, EPL <= 10 ? 4 : 0) layernorm_kernel(const void* __restrict__ x_, long long rows,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, __nv_bfloat16* __restrict__ y) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int C = EPL * 32;
     constexpr int VEC = (EPL % 4 == 0) ? 4 : 2;          // floats per vector access
     constexpr int NV = EPL / VEC;
@@ -487,6 +495,8 @@ template <bool IN_F32>
 __global__ void __launch_bounds__(256) layernorm_generic_kernel(const void* __restrict__ x_, long long rows, int C,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 float eps, __nv_bfloat16* __restrict__ y) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int MAXV = 12;                     // 12 * 32 lanes * 4 = 1536 channels max
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -534,6 +544,8 @@ __global__ void __launch_bounds__(256) layernorm_generic_kernel(const void* __re
 
 // ---------------------------------------------------------------------------------------------- row softmax (bf16, in place)
 __global__ void __launch_bounds__(256) softmax_rows_kernel(__nv_bfloat16* x, int cols, long long ld) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[8];
     __nv_bfloat16* row = x + (long long)blockIdx.x * ld;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -569,14 +581,11 @@ extern "C" int rg_groupnorm_stats(const rg_gn_t* g, rg_stream_t stream) {
     int rc = fill_gn(g, p, grid, threads);
     if (rc) return rc;
     const size_t smem = ((size_t)threads * 16 + (size_t)p.C * 2) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(gn_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        cudaFuncSetAttribute(gn_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr_done = true;
-    }
-    if (p.in_f32) gn_stats_kernel<true><<<grid, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-    else gn_stats_kernel<false><<<grid, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    static std::atomic<bool> done_t[kMaxDevices], done_f[kMaxDevices];
+    if ((rc = ensure_smem_attr(reinterpret_cast<const void*>(&gn_stats_kernel<true>), 96 * 1024, done_t, "cudaFuncSetAttribute(gn_stats_kernel)"))) return rc;
+    if ((rc = ensure_smem_attr(reinterpret_cast<const void*>(&gn_stats_kernel<false>), 96 * 1024, done_f, "cudaFuncSetAttribute(gn_stats_kernel)"))) return rc;
+    if (p.in_f32) launch_kernel<1>(gn_stats_kernel<true>, dim3(grid), dim3(threads), smem, reinterpret_cast<cudaStream_t>(stream), p);
+    else launch_kernel<1>(gn_stats_kernel<false>, dim3(grid), dim3(threads), smem, reinterpret_cast<cudaStream_t>(stream), p);
     count_launch();
     return check_launch("gn_stats_kernel");
 }
@@ -587,8 +596,8 @@ extern "C" int rg_groupnorm_apply(const rg_gn_t* g, rg_stream_t stream) {
     int rc = fill_gn(g, p, grid, threads);
     if (rc) return rc;
     if (!g->y) return set_error(RG_ERR_ARG, "groupnorm_apply: null output");
-    if (p.in_f32) gn_apply_kernel<true><<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-    else gn_apply_kernel<false><<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    if (p.in_f32) launch_kernel<1>(gn_apply_kernel<true>, dim3(grid), dim3(threads), 0, reinterpret_cast<cudaStream_t>(stream), p);
+    else launch_kernel<1>(gn_apply_kernel<false>, dim3(grid), dim3(threads), 0, reinterpret_cast<cudaStream_t>(stream), p);
     count_launch();
     return check_launch("gn_apply_kernel");
 }
@@ -601,16 +610,13 @@ extern "C" int rg_groupnorm(const rg_gn_t* g, rg_stream_t stream) {
         int rc = fill_gn(g, p, grid, threads);
         if (rc) return rc;
         if (!g->y) return set_error(RG_ERR_ARG, "groupnorm: null output");
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaFuncSetAttribute(gn_fused_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnFusedMaxSmem);
-            cudaFuncSetAttribute(gn_fused_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnFusedMaxSmem);
-            attr_done = true;
-        }
+        static std::atomic<bool> done_t[kMaxDevices], done_f[kMaxDevices];
+        if ((rc = ensure_smem_attr(reinterpret_cast<const void*>(&gn_fused_small_kernel<true>), (int)kGnFusedMaxSmem, done_t, "cudaFuncSetAttribute(gn_fused_small_kernel)"))) return rc;
+        if ((rc = ensure_smem_attr(reinterpret_cast<const void*>(&gn_fused_small_kernel<false>), (int)kGnFusedMaxSmem, done_f, "cudaFuncSetAttribute(gn_fused_small_kernel)"))) return rc;
         const size_t smem = (size_t)p.HW * p.cpg * (p.in_f32 ? 4 : 2);
         const dim3 fgrid((unsigned)p.groups, (unsigned)p.N);
-        if (p.in_f32) gn_fused_small_kernel<true><<<fgrid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-        else gn_fused_small_kernel<false><<<fgrid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+        if (p.in_f32) launch_kernel<1>(gn_fused_small_kernel<true>, dim3(fgrid), dim3(256), smem, reinterpret_cast<cudaStream_t>(stream), p);
+        else launch_kernel<1>(gn_fused_small_kernel<false>, dim3(fgrid), dim3(256), smem, reinterpret_cast<cudaStream_t>(stream), p);
         count_launch();
         return check_launch("gn_fused_small_kernel");
     }
@@ -625,7 +631,7 @@ static void launch_ln(const void* x, int64_t rows, const float* gamma, const flo
     long long blocks = (rows + wpb - 1) / wpb;
     const long long cap = (long long)sm_count() * 8;       // persistent: each warp walks rows with a one-row prefetch
     if (blocks > cap) blocks = cap;
-    layernorm_kernel<IN_F32, EPL><<<(unsigned)blocks, wpb * 32, 0, s>>>(x, rows, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y));
+    launch_kernel(layernorm_kernel<IN_F32, EPL>, dim3((unsigned)blocks), dim3(wpb * 32), 0, s, x, rows, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y));
 }
 
 extern "C" int rg_layernorm(const void* x, int32_t in_dtype, int64_t rows, int32_t C, const float* gamma,
@@ -640,8 +646,8 @@ extern "C" int rg_layernorm(const void* x, int32_t in_dtype, int64_t rows, int32
     else {
         const int wpb = 8;
         const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-        if (f32) layernorm_generic_kernel<true><<<grid, wpb * 32, 0, s>>>(x, rows, C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y));
-        else layernorm_generic_kernel<false><<<grid, wpb * 32, 0, s>>>(x, rows, C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y));
+        if (f32) launch_kernel(layernorm_generic_kernel<true>, dim3(grid), dim3(wpb * 32), 0, s, x, rows, C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y));
+        else launch_kernel(layernorm_generic_kernel<false>, dim3(grid), dim3(wpb * 32), 0, s, x, rows, C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y));
     }
     count_launch();
     return check_launch("layernorm_kernel");
@@ -649,7 +655,7 @@ extern "C" int rg_layernorm(const void* x, int32_t in_dtype, int64_t rows, int32
 
 extern "C" int rg_softmax_rows(void* x, int64_t rows, int32_t cols, int64_t ld, rg_stream_t stream) {
     if (!x) return set_error(RG_ERR_ARG, "softmax_rows: null pointer");
-    softmax_rows_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    launch_kernel(softmax_rows_kernel, dim3((unsigned)rows), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
         reinterpret_cast<__nv_bfloat16*>(x), cols, ld);
     count_launch();
     return check_launch("softmax_rows_kernel");

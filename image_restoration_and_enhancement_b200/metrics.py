@@ -6,8 +6,11 @@ channel_axis=2)``) -- scikit-image itself is not installed here -- in float64 nu
 is the reference's statistics block (``:338-346``).  ``gather_per_image`` is the multi-GPU piece: every rank
 contributes its per-image float64 values with their global indices, rank 0 reorders by index and aggregates, so
 the result is bit-identical to a single-process run (partial sums are never all-reduced).
-LPIPS needs pretrained AlexNet + linear heads that are not available offline: ``use_lpips`` is accepted for API
-parity and yields ``None`` values unless a callable is supplied.
+LPIPS (``src/metrics.py:67,97-111``): on a CUDA device ``use_lpips=True`` scores with ``lpips.LPIPSB200`` (AlexNet taps on
+the tcgen05 conv kernel); the pretrained AlexNet + lin-head files are not available offline, so unless
+``lpips_weights=(alexnet_state_dict_path, lpips_alex_pth_path)`` is given the network is the seeded random-init one and
+the calculator says so loudly (values unpinned, bookkeeping exact).  On the CPU LPIPS needs ``lpips_fn`` (a callable);
+without one a warning is printed, as the reference does when the ``lpips`` package is missing (``:24-29``).
 
 ``psnr_ssim_device`` is the GPU metric pass (SURVEY 8f "f2"): the predictions never leave HBM, the kernels in
 ``csrc/metrics.cu`` reproduce the float64 operation ORDER of scipy's uniform filter and numpy's mean, and the values
@@ -143,12 +146,27 @@ class MetricsCalculator:
     bits as "cpu" -- and raises if librestoragen.so or a GPU is missing (no silent fallback)."""
 
     def __init__(self, use_lpips: bool = True, use_fid: bool = False, device: str = "cpu",
-                 lpips_fn: Callable[[np.ndarray, np.ndarray], float] | None = None):
+                 lpips_fn: Callable[[np.ndarray, np.ndarray], float] | None = None, lpips_weights=None, lpips_seed: int = 0):
+        import sys
         self.lpips_fn = lpips_fn
-        self.use_lpips = use_lpips and lpips_fn is not None
         self.use_fid = False              # FID needs Inception weights that are not available offline
         self.device = device
         self._gpu = str(device).startswith("cuda")
+        self._lpips_model = None
+        if use_lpips and lpips_fn is None and self._gpu:
+            from . import lpips as _lp
+            if lpips_weights is not None:
+                import torch
+                a, l = (torch.load(str(f), map_location="cpu") for f in lpips_weights)
+                sd = _lp.load_lpips_state_dict(a, l)
+            else:
+                print("Warning: pretrained LPIPS (AlexNet) weights are not available offline -- using the seeded random-init "
+                      f"network (seed {lpips_seed}); LPIPS VALUES are not comparable with published ones", file=sys.stderr)
+                sd = _lp.random_lpips_state_dict(lpips_seed)
+            self._lpips_model = _lp.LPIPSB200(sd, device=str(device))
+        elif use_lpips and lpips_fn is None:
+            print("Warning: LPIPS not available on the CPU path (no lpips_fn given); use device='cuda'", file=sys.stderr)
+        self.use_lpips = use_lpips and (lpips_fn is not None or self._lpips_model is not None)
 
     def _device_pair(self, pred: np.ndarray, gt: np.ndarray) -> tuple[float, float]:
         import torch
@@ -167,7 +185,12 @@ class MetricsCalculator:
     def calculate_lpips(self, pred: np.ndarray, gt: np.ndarray):
         if not self.use_lpips:
             return None
-        return float(self.lpips_fn(_match_shape(pred, gt), gt))
+        pred = _match_shape(pred, gt)
+        if self.lpips_fn is not None:
+            return float(self.lpips_fn(pred, gt))
+        import torch
+        to3 = lambda a: np.ascontiguousarray(np.repeat(a[..., None], 3, axis=2) if a.ndim == 2 else a)
+        return self._lpips_model(torch.from_numpy(to3(pred)[None]).to(self.device), torch.from_numpy(to3(gt)[None]).to(self.device))[0]
 
     def calculate_delta_e(self, pred: np.ndarray, gt: np.ndarray, use_delta_e2000: bool = False) -> float:
         """Mean Delta-E 76 in CIELAB (reference ``src/metrics.py:113-148``; its ``use_delta_e2000`` branch computes the

@@ -13,7 +13,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (RG_ACT_GEGLU, RG_ACT_NONE, RG_ACT_SILU, RG_DT_BF16, RG_DT_F16, RG_DT_F32, RgAct, RgAttn, RgConv, RgGn,
+from ._lib import (RG_ACT_GEGLU, RG_ACT_NONE, RG_ACT_RELU, RG_ACT_SILU, RG_DT_BF16, RG_DT_F16, RG_DT_F32, RgAct, RgAttn, RgConv, RgGn,
                    RgSched, check)
 
 bf16, f32, f16 = torch.bfloat16, torch.float32, torch.float16
@@ -59,6 +59,22 @@ def _gn_workspace(device, N: int, groups: int) -> torch.Tensor:
     if ws is None:
         full = GN_MAX_IMAGES + GN_WS_MAX_IMAGES * 32 * 2 + GN_WS_MAX_IMAGES * GN_MAX_BLOCKS * 32 * 2
         ws = _GN_WS[key] = torch.zeros((full,), dtype=f32, device=device)
+    return ws
+
+
+# Deterministic split-K workspace of rg_conv2d (include/restoragen.h: rg_conv_t.splitk_ws): arrival counters + fp32 partial
+# tiles.  One zero-initialised buffer per device, allocated once (captured graphs keep its address); 512 MiB covers UNet
+# batches up to ~96 at every level -- HBM is 180 GB.  SPLITK = False switches the split off (A/B measurements only).
+SPLITK = True
+SPLITK_WS_BYTES = (256 << 10) + (512 << 20)
+_SPLITK_WS: dict = {}
+
+
+def _splitk_workspace(device) -> torch.Tensor:
+    key = (device.type, device.index)
+    ws = _SPLITK_WS.get(key)
+    if ws is None:
+        ws = _SPLITK_WS[key] = torch.zeros((SPLITK_WS_BYTES,), dtype=torch.uint8, device=device)
     return ws
 
 
@@ -147,6 +163,9 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, *, kh: int = 1, kw: int = 1, stride
         p.out_f32 = out_f32.data_ptr()
     p.out_stride_n, p.out_stride_h, p.out_stride_w = out_strides
     p.act, p.scale = act, scale
+    if SPLITK:
+        ws = _splitk_workspace(x.device)
+        p.splitk_ws, p.splitk_ws_bytes = ws.data_ptr(), ws.numel()
     e0 = _prof_begin()
     check(lib.rg_conv2d(C.byref(p), _stream()), "rg_conv2d")
     _prof_end(e0, 2.0 * N * OH * OW * Cout * ktot, "gemm",
@@ -155,10 +174,14 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, *, kh: int = 1, kw: int = 1, stride
     return out_bf16, out_f32
 
 
-def linear(x: torch.Tensor, w: torch.Tensor, **kw):
-    """x bf16 [M, K] (row stride arbitrary multiple of 8) -> [M, N]; same epilogue options as conv2d."""
+def linear(x: torch.Tensor, w: torch.Tensor, images: int = 1, **kw):
+    """x bf16 [M, K] (row stride arbitrary multiple of 8) -> [M, N]; same epilogue options as conv2d.
+    ``images``: the M rows are ``images`` equal groups of tokens (one per image).  It only tells the kernel the
+    per-image geometry, which is what its split-K decision may depend on (results stay independent of the batch size)."""
     M, K = x.shape
-    x4 = x.as_strided((1, 1, M, K), (0, 0, x.stride(0), 1))
+    assert M % images == 0
+    rows = M // images
+    x4 = x.as_strided((images, 1, rows, K), (rows * x.stride(0), 0, x.stride(0), 1))
     ob, of = conv2d(x4, w, **kw)
     return (None if ob is None else ob.view(M, -1)), (None if of is None else of.view(M, -1))
 
@@ -382,3 +405,24 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     y = torch.empty(x.shape, dtype=bf16, device=x.device)
     check(_lib.load().rg_cast_f32_bf16(x.data_ptr(), x.numel(), y.data_ptr(), _stream()), "rg_cast_f32_bf16")
     return y
+
+
+def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
+    """MaxPool2d(3, stride=2) on bf16 channels-last [N,H,W,C]."""
+    N, H, W, Cc = x.shape
+    assert x.dtype == bf16 and x.is_contiguous()
+    y = torch.empty((N, (H - 3) // 2 + 1, (W - 3) // 2 + 1, Cc), dtype=bf16, device=x.device)
+    check(_lib.load().rg_maxpool3x3s2(x.data_ptr(), N, H, W, Cc, y.data_ptr(), _stream()), "rg_maxpool3x3s2")
+    return y
+
+
+def lpips_layer(f0: torch.Tensor, f1: torch.Tensor, lin: torch.Tensor) -> torch.Tensor:
+    """One LPIPS feature level: f0, f1 bf16 [N,H,W,C], lin f32 [C] -> f32 [N, blocks] partial sums (see restoragen.h)."""
+    N, H, W, Cc = f0.shape
+    assert f0.dtype == bf16 and f1.dtype == bf16 and f0.is_contiguous() and f1.is_contiguous() and f1.shape == f0.shape
+    assert lin.dtype == f32 and lin.is_contiguous() and lin.numel() == Cc
+    lib = _lib.load()
+    out = torch.empty((N, lib.rg_lpips_layer_blocks(H * W)), dtype=f32, device=f0.device)
+    check(lib.rg_lpips_layer(f0.data_ptr(), f1.data_ptr(), lin.data_ptr(), N, H * W, Cc, out.data_ptr(), _stream()),
+          "rg_lpips_layer")
+    return out

@@ -32,30 +32,38 @@ def shard(n_items: int, rank: int, world: int) -> list[int]:
 TASK_DIR = {"denoise": "denoise", "sr": "sr_x4", "colorize": "colorize", "inpaint": "inpaint"}
 
 
-def _score(preds: list[np.ndarray], gts: list[np.ndarray], backend: str) -> tuple[list[float], list[float]]:
-    """Per-image PSNR / SSIM.  "gpu": csrc/metrics.cu on the uploaded u8 batch; "cpu": the numpy/scipy bookkeeping.
-    Both give the same float64 bits (tests/test_kernels_gpu.py::metrics_*)."""
+def _score(preds: list[np.ndarray], gts: list[np.ndarray], backend: str, lpips_model=None) -> dict[str, list[float]]:
+    """Per-image PSNR / SSIM (/ LPIPS).  "gpu": csrc/metrics.cu (+ lpips.LPIPSB200) on the uploaded u8 batch; "cpu": the
+    numpy/scipy bookkeeping.  PSNR / SSIM give the same float64 bits either way (tests/test_kernels_gpu.py::metrics_*);
+    LPIPS exists on the GPU only."""
     preds = [metrics._match_shape(p, g) for p, g in zip(preds, gts)]
     if backend == "gpu":
-        psnrs, ssims = [None] * len(preds), [None] * len(preds)
+        out: dict[str, list] = {"psnr": [None] * len(preds), "ssim": [None] * len(preds)}
+        if lpips_model is not None:
+            out["lpips"] = [None] * len(preds)
         by_shape: dict[tuple, list[int]] = {}
         for i, g in enumerate(gts):
             by_shape.setdefault(g.shape, []).append(i)
         for idx in by_shape.values():
-            p, s = metrics.psnr_ssim_device(torch.from_numpy(np.stack([preds[i] for i in idx])).cuda(),
-                                            torch.from_numpy(np.stack([gts[i] for i in idx])).cuda())
+            pd = torch.from_numpy(np.stack([preds[i] for i in idx])).cuda()
+            gd = torch.from_numpy(np.stack([gts[i] for i in idx])).cuda()
+            p, s = metrics.psnr_ssim_device(pd, gd)
+            lp = lpips_model(pd, gd) if lpips_model is not None else None
             for j, i in enumerate(idx):
-                psnrs[i], ssims[i] = p[j], s[j]
-        return psnrs, ssims
+                out["psnr"][i], out["ssim"][i] = p[j], s[j]
+                if lp is not None:
+                    out["lpips"][i] = lp[j]
+        return out
     if backend != "cpu":
         raise ValueError(f"unknown metrics backend {backend}")
     calc = metrics.MetricsCalculator(use_lpips=False)
-    return ([calc.calculate_psnr(p, g) for p, g in zip(preds, gts)], [calc.calculate_ssim(p, g) for p, g in zip(preds, gts)])
+    return {"psnr": [calc.calculate_psnr(p, g) for p, g in zip(preds, gts)],
+            "ssim": [calc.calculate_ssim(p, g) for p, g in zip(preds, gts)]}
 
 
 def run_task(pipe, task: str, n_images: int, rank: int = 0, world: int = 1, size: int = 512, batch: int | None = None,
-             handoff_mode: str = "memory", metrics_backend: str = "gpu", workdir=None, overlap: bool = True
-             ) -> tuple[list[int], dict[str, list[float]], float]:
+             handoff_mode: str = "memory", metrics_backend: str = "gpu", workdir=None, overlap: bool = True,
+             lpips_model=None) -> tuple[list[int], dict[str, list[float]], float]:
     """Predict + score this rank's share of one task.
 
     ``handoff_mode`` selects what sits between the pipeline and the metrics (see handoff.py):
@@ -120,17 +128,21 @@ def run_task(pipe, task: str, n_images: int, rank: int = 0, world: int = 1, size
             for o, nm in zip(outs, names):
                 handoff.save_prediction(o, pred_dir / nm)                                # generate_predictions.py:83-84
             preds = [handoff.load_image(pred_dir / nm) for nm in names]
-        return _score(preds, gts, metrics_backend)
+        return _score(preds, gts, metrics_backend, lpips_model)
 
     batches = [mine[s:s + bsz] for s in range(0, len(mine), bsz)]
     vals: dict[str, list[float]] = {"psnr": [], "ssim": []}
+    if lpips_model is not None and metrics_backend == "gpu":
+        vals["lpips"] = []
+
+    def collect(d):
+        for k, v in d.items():
+            vals[k] += v
     t0 = time.time()
     if not overlap or len(batches) < 2:
         for idx in batches:
             names, ims, gts, masks = prepare(idx)
-            p, q = score(pipe.process_batch(ims, task, masks=masks), names, gts)
-            vals["psnr"] += p
-            vals["ssim"] += q
+            collect(score(pipe.process_batch(ims, task, masks=masks), names, gts))
         return mine, vals, time.time() - t0
     # Software pipeline over batches: while the GPU samples batch k, one host thread prepares batch k+1 (synthesis,
     # codecs) and another scores batch k-1 (codec round trip, metric kernels on the default stream).  PIL / OpenCV /
@@ -150,25 +162,29 @@ def run_task(pipe, task: str, n_images: int, rank: int = 0, world: int = 1, size
             outs = pipe.process_batch(ims, task, masks=masks)
             pending.append(pool.submit(score, outs, names, gts))
         for f in pending:
-            p, q = f.result()
-            vals["psnr"] += p
-            vals["ssim"] += q
+            collect(f.result())
     return mine, vals, time.time() - t0
 
 
 def run_sweep(n_images: int = 100, tasks=TASKS, size: int = 512, seed: int = 42, random_init: int = 0,
-              handoff_mode: str = "memory", metrics_backend: str = "gpu", workdir=None) -> dict | None:
-    """Call from every rank (torchrun).  Returns the evaluation dict on rank 0, None elsewhere."""
+              handoff_mode: str = "memory", metrics_backend: str = "gpu", workdir=None, use_lpips: bool = True,
+              lpips_seed: int = 0) -> dict | None:
+    """Call from every rank (torchrun).  Returns the evaluation dict on rank 0, None elsewhere.  ``use_lpips``: per-image
+    LPIPS next to PSNR / SSIM (GPU metric backend; seeded random-init AlexNet, the same on every rank -- see lpips.py)."""
     import torch.distributed as dist
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     cfg = {t: {"fine_tuned_dir": "nonexistent", "pretrained_id": "", "random_init": random_init + (1000 if t == "inpaint" else 0)}
            for t in TASKS}
     pipe = RestorationPipeline(device="cuda", config=cfg, seed=seed, strict=True)
+    lp = None
+    if use_lpips and metrics_backend == "gpu":
+        from .lpips import LPIPSB200, random_lpips_state_dict
+        lp = LPIPSB200(random_lpips_state_dict(lpips_seed), device=f"cuda:{torch.cuda.current_device()}")
     results = {}
     for task in tasks:
         idx, vals, secs = run_task(pipe, task, n_images, rank, world, size, handoff_mode=handoff_mode,
-                                   metrics_backend=metrics_backend, workdir=workdir)
+                                   metrics_backend=metrics_backend, workdir=workdir, lpips_model=lp)
         full = metrics.gather_per_image(idx, vals)
         if rank == 0:
             results[task] = metrics.summarize(task, full, n_images)

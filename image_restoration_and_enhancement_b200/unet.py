@@ -143,7 +143,7 @@ class UNetB200:
             buf = t.kv_bufs.get((Bu, T))
             if buf is None:
                 buf = t.kv_bufs[(Bu, T)] = torch.empty((Bu, T, 2 * t.C), dtype=f16, device=self.device)
-            ops.linear(c, t.w_kv2, out_bf16=buf.view(1, 1, Bu * T, 2 * t.C))
+            ops.linear(c, t.w_kv2, images=Bu, out_bf16=buf.view(Bu, 1, T, 2 * t.C))
             t.kv = buf
         self.ctx_batch = Bu
 
@@ -175,20 +175,20 @@ class UNetB200:
         tok = tok.view(M, Cc)
         # self-attention
         l1 = ops.layernorm(tok, *t.ln[0])
-        qkv, _ = ops.linear(l1, t.w_qkv, out_bf16=True, out_half=f16)         # attention operands in fp16 (like the reference)
+        qkv, _ = ops.linear(l1, t.w_qkv, images=N, out_bf16=True, out_half=f16)         # attention operands in fp16 (like the reference)
         qkv = qkv.view(N, H * W, 3, heads, d)
         o = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], d ** -0.5)
-        ops.linear(o.view(M, Cc), t.w_o1, bias=t.b_o1, res=tok, out_f32=tok.view(1, 1, M, Cc))
+        ops.linear(o.view(M, Cc), t.w_o1, images=N, bias=t.b_o1, res=tok, out_f32=tok.view(N, 1, H * W, Cc))
         # cross-attention against the cached prompt K/V
         l2 = ops.layernorm(tok, *t.ln[1])
-        q2, _ = ops.linear(l2, t.w_q2, out_bf16=True, out_half=f16)
+        q2, _ = ops.linear(l2, t.w_q2, images=N, out_bf16=True, out_half=f16)
         kv = t.kv.view(N, -1, 2, heads, d)
         o2 = ops.attention(q2.view(N, H * W, heads, d), kv[:, :, 0], kv[:, :, 1], d ** -0.5)
-        ops.linear(o2.view(M, Cc), t.w_o2, bias=t.b_o2, res=tok, out_f32=tok.view(1, 1, M, Cc))
+        ops.linear(o2.view(M, Cc), t.w_o2, images=N, bias=t.b_o2, res=tok, out_f32=tok.view(N, 1, H * W, Cc))
         # GEGLU feed-forward
         l3 = ops.layernorm(tok, *t.ln[2])
-        gg, _ = ops.linear(l3, t.w_gg, bias=t.b_gg, act=RG_ACT_GEGLU, out_bf16=True)
-        tb, _ = ops.linear(gg, t.w_ff, bias=t.b_ff, res=tok, out_bf16=True)
+        gg, _ = ops.linear(l3, t.w_gg, images=N, bias=t.b_gg, act=RG_ACT_GEGLU, out_bf16=True)
+        tb, _ = ops.linear(gg, t.w_ff, images=N, bias=t.b_ff, res=tok, out_bf16=True)
         ob, of = ops.conv2d(tb.view(N, H, W, Cc), t.w_out, bias=t.b_out, res=x, out_f32=True, out_bf16=want_bf16)
         return of, ob
 
@@ -216,9 +216,9 @@ class UNetB200:
         n_mod, h, w, cin = latents.shape
         assert cin == self.in_channels and Bu % n_mod == 0 and timesteps.shape[0] == Bu
         te = ops.timestep_embedding(timesteps, 320)
-        e1, _ = ops.linear(te, self.w_t1, bias=self.b_t1, act=RG_ACT_SILU, out_bf16=True)
-        e2, _ = ops.linear(e1, self.w_t2, bias=self.b_t2, act=RG_ACT_SILU, out_bf16=True)     # silu(temb)
-        _, temb_all = ops.linear(e2, self.w_temb, bias=self.b_temb, out_f32=True)
+        e1, _ = ops.linear(te, self.w_t1, images=Bu, bias=self.b_t1, act=RG_ACT_SILU, out_bf16=True)
+        e2, _ = ops.linear(e1, self.w_t2, images=Bu, bias=self.b_t2, act=RG_ACT_SILU, out_bf16=True)     # silu(temb)
+        _, temb_all = ops.linear(e2, self.w_temb, images=Bu, bias=self.b_temb, out_f32=True)
 
         cols = ops.im2col_small(latents, Bu, 3, 1, 1, h, w, self.kpad_in)
         _, x = ops.conv2d(cols, self.w_conv_in, bias=self.b_conv_in, out_f32=True)

@@ -116,7 +116,7 @@ class VAEB200:
         Tp = (T + 7) // 8 * 8                                   # row pitch of the score matrix (16-B aligned rows)
         y, _ = ops.groupnorm(x, a.gn_g, a.gn_b, eps=1e-6, silu=False)
         y2 = y.view(N * T, Cc)
-        qk, _ = ops.linear(y2, a.w_qk, bias=a.b_qk, out_bf16=True)              # [N*T, 2C]
+        qk, _ = ops.linear(y2, a.w_qk, images=N, bias=a.b_qk, out_bf16=True)              # [N*T, 2C]
         out = torch.empty_like(x)
         S = torch.empty((T, Tp), dtype=bf16, device=x.device)
         vt = torch.empty((Cc, Tp), dtype=bf16, device=x.device)

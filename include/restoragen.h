@@ -41,6 +41,7 @@ typedef void* rg_stream_t; /* cudaStream_t */
 #define RG_ACT_NONE 0
 #define RG_ACT_SILU 1
 #define RG_ACT_GEGLU 2          /* columns interleaved 16 value | 16 gate per 32-wide unit; output width = Cout/2 */
+#define RG_ACT_RELU 3           /* the AlexNet feature convolutions of LPIPS (src/metrics.py:97-111) */
 
 #define RG_DT_BF16 0
 #define RG_DT_F32 1
@@ -51,6 +52,11 @@ int rg_version(void);
 /* number of kernel launches issued by this library in the calling process (all threads) */
 int64_t rg_launch_count(void);
 int rg_device_sm_count(void);
+/* Programmatic dependent launch between consecutive kernels of this library (default on): the next kernel's launch
+   latency and prologue overlap the running kernel; every kernel waits for its predecessor before it touches global
+   memory, so results are unchanged.  mode: bit 0 = GEMM / attention / glue kernels, bit 1 = GroupNorm kernels; 0 = plain
+   stream serialization.  Returns the previous mode.  Process-wide; set before capturing CUDA graphs. */
+int rg_set_pdl(int mode);
 
 /* ---------------------------------------------------------------------------------------------
  * K1-K4  implicit-GEMM convolution / linear layer on tcgen05 (TMEM accumulators, TMA operand loads).
@@ -92,7 +98,19 @@ typedef struct rg_conv {
     float scale;
     int32_t out16_dtype;   /* element type written through out_bf16: RG_DT_BF16 (default) or RG_DT_F16 (the attention
                               operands q, k, v: fp16 like the reference's CUDA path, src/inference.py:57) */
+    /* Optional split-K workspace (NULL = never split).  Few-pixel layers with a long K (the 32x32-and-below levels
+       of the UNet at small batch) cannot fill 148 SMs with output tiles alone, so K is cut into 2..8 slices computed
+       by different CTA pairs; every slice writes its fp32 partial tile here and the LAST slice to arrive (a per-tile
+       arrival counter at the head of the workspace elects it) adds the partials IN SLICE ORDER and runs the normal
+       epilogue -- the result is bitwise reproducible and, because the slice count depends on the per-image geometry
+       only (OH*OW, K, Cout), independent of the batch size.  The workspace must be ZERO when first used (the
+       counters reset themselves), at least RG_SPLITK_WS_MIN_BYTES, and is shared by all calls of one stream. */
+    void* splitk_ws;
+    int64_t splitk_ws_bytes;
 } rg_conv_t;
+
+#define RG_SPLITK_COUNTER_BYTES (256 * 1024)
+#define RG_SPLITK_WS_MIN_BYTES (RG_SPLITK_COUNTER_BYTES + (32ll << 20))
 
 int rg_conv2d(const rg_conv_t* p, rg_stream_t stream);
 
@@ -273,6 +291,23 @@ int rg_metrics_sse_u8(const uint8_t* pred, const uint8_t* gt, int32_t N, int64_t
 int rg_metrics_ssim_chunks(int32_t H, int32_t W);   /* number of partial sums per (image, channel); -1 if unsupported */
 int rg_metrics_ssim_u8(const uint8_t* pred, const uint8_t* gt, int32_t N, int32_t H, int32_t W, int32_t C, double c1,
                        double c2, double cov_norm, double* smap_ws, double* chunk_sums, rg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LPIPS (AlexNet) glue -- the learned perceptual metric of the reference's evaluator
+ *   (src/metrics.py:67 lpips.LPIPS(net='alex'), :97-111 calculate_lpips).  The five feature convolutions run on
+ *   rg_conv2d with RG_ACT_RELU; these two kernels are the rest of the graph.
+ *   rg_maxpool3x3s2: bf16 [N,H,W,C] -> bf16 [N,(H-3)/2+1,(W-3)/2+1,C]  (MaxPool2d(3, stride 2)), C % 8 == 0.
+ *   rg_lpips_layer:  f0, f1 bf16 [N][HW][C] post-ReLU features of the two images, lin fp32 [C] (the non-negative 1x1
+ *     head); partial[n][b] (b < rg_lpips_layer_blocks(HW)) = sum over block b's pixels of
+ *     sum_c lin[c] * (f0/(||f0||_2 + 1e-10) - f1/(||f1||_2 + 1e-10))^2.  The caller adds the partials of an image in
+ *     block order and divides by HW (spatial average); the split depends on HW only, so the value of an image does not
+ *     depend on the batch size.
+ * ------------------------------------------------------------------------------------------- */
+#define RG_LPIPS_MAX_BLOCKS 256
+int rg_maxpool3x3s2(const void* x, int32_t N, int32_t H, int32_t W, int32_t C, void* y, rg_stream_t stream);
+int rg_lpips_layer_blocks(int32_t HW);
+int rg_lpips_layer(const void* f0, const void* f1, const float* lin, int32_t N, int32_t HW, int32_t C, float* partial,
+                   rg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -67,6 +67,85 @@ def case_linear(M=256, K=128, N=160, bias=True, res=None, act=RG_ACT_NONE, f32_o
     return rel_l2(out, ref), (TOL_F32 if f32_out else TOL_BF16)
 
 
+def case_splitk_invariance(seed=130):
+    """Deterministic split-K (epilogue_splitk): the slice count depends on the per-image geometry only and the partials
+    are added in slice order, so (a) two runs give the same bits and (b) an image alone gives the same bits as inside a
+    batch -- for a 3x3 conv at the 8x8 level (8 slices), one at 16x16 (4 slices, bf16 out) and a token linear
+    (images=..., 4 slices).  Returns the number of mismatching comparisons (tolerance 0)."""
+    _setup()
+    bad = 0
+    for (H, W, Cin, Cout, f32_out) in ((8, 8, 1280, 1280, True), (16, 16, 1280, 640, False)):
+        x = _rand((5, H, W, Cin), seed)
+        w = pack_w(_rand((Cout, Cin, 3, 3), seed + 1, 1.0 / math.sqrt(Cin * 9)))
+        b = _rand((Cout,), seed + 2, 0.5, torch.float32)
+        r = _rand((5, H, W, Cout), seed + 3, 1.0, torch.float32)
+        kw = dict(kh=3, kw=3, pad_t=1, pad_l=1, bias=b, out_bf16=not f32_out, out_f32=f32_out)
+        pick = (lambda o: o[1]) if f32_out else (lambda o: o[0])
+        full = pick(ops.conv2d(x, w, res=r, **kw))
+        again = pick(ops.conv2d(x, w, res=r, **kw))
+        one = pick(ops.conv2d(x[3:4].contiguous(), w, res=r[3:4].contiguous(), **kw))
+        torch.cuda.synchronize()
+        bad += int(not torch.equal(full, again)) + int(not torch.equal(full[3:4], one))
+    xt = _rand((3 * 256, 5120), seed + 5)
+    wt = _rand((1280, 5120), seed + 6, 1.0 / math.sqrt(5120))
+    rt = _rand((3 * 256, 1280), seed + 7, 1.0, torch.float32)
+    full, _ = ops.linear(xt, wt, images=3, res=rt, out_bf16=True)
+    one, _ = ops.linear(xt[256:512].contiguous(), wt, images=1, res=rt[256:512].contiguous(), out_bf16=True)
+    ref = xt.float() @ wt.float().t() + rt
+    torch.cuda.synchronize()
+    bad += int(not torch.equal(full[256:512], one)) + int(rel_l2(full, ref) > TOL_BF16)
+    return float(bad), 0.0
+
+
+def case_conv_relu(seed=140):
+    """RG_ACT_RELU (the LPIPS feature convs) through the three epilogue flavours: TMA run-time-flag (Cout 256 and 64),
+    direct stores (Cout 192 / 384: not a multiple of the column tile)."""
+    from image_restoration_and_enhancement_b200._lib import RG_ACT_RELU
+    _setup()
+    worst = 0.0
+    for i, (Cin, Cout, k) in enumerate(((256, 256, 3), (384, 64, 1), (192, 384, 3), (1600, 192, 1))):
+        x = _rand((2, 15, 17, Cin), seed + 4 * i)
+        w = _rand((Cout, Cin, k, k), seed + 4 * i + 1, 1.0 / math.sqrt(Cin * k * k))
+        b = _rand((Cout,), seed + 4 * i + 2, 0.5, torch.float32)
+        ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=k // 2))
+        ob, _ = ops.conv2d(x, pack_w(w), kh=k, kw=k, pad_t=k // 2, pad_l=k // 2, bias=b, act=RG_ACT_RELU, out_bf16=True)
+        torch.cuda.synchronize()
+        worst = max(worst, rel_l2(ob.float().permute(0, 3, 1, 2), ref))
+        assert float(ob.float().min()) >= 0.0
+    return worst, TOL_BF16
+
+
+def case_maxpool(seed=150):
+    _setup()
+    x = _rand((3, 31, 127, 64), seed)
+    ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2).permute(0, 2, 3, 1)
+    y = ops.maxpool3x3s2(x)
+    torch.cuda.synchronize()
+    return float((y.float() - ref).abs().max()), 0.0
+
+
+def case_lpips_layer(seed=160):
+    """normalise / diff / lin head / spatial sum of one LPIPS level vs the torch expression on the same bf16 features;
+    and an image's partial sums do not depend on the batch it sits in."""
+    _setup()
+    worst = 0.0
+    for (H, W, Cc) in ((31, 31, 384), (127, 127, 64), (7, 9, 256)):
+        f0 = F.relu(_rand((3, H, W, Cc), seed)).contiguous()
+        f1 = F.relu(_rand((3, H, W, Cc), seed + 1)).contiguous()
+        lin = _rand((Cc,), seed + 2, 1.0, torch.float32).abs().contiguous()
+        part = ops.lpips_layer(f0, f1, lin)
+        one = ops.lpips_layer(f0[1:2].contiguous(), f1[1:2].contiguous(), lin)
+        torch.cuda.synchronize()
+        a, b = f0.float(), f1.float()
+        na = a / (a.pow(2).sum(-1, keepdim=True).sqrt() + 1e-10)
+        nb = b / (b.pow(2).sum(-1, keepdim=True).sqrt() + 1e-10)
+        ref = ((na - nb).pow(2) * lin).sum(dim=(1, 2, 3))
+        got = part.double().sum(dim=1).float()
+        worst = max(worst, rel_l2(got, ref))
+        assert torch.equal(part[1:2], one)
+    return worst, 2e-5
+
+
 def case_geglu(M=300, K=320, C4=1280, seed=5):
     """ff.net.0 (GEGLU): proj -> chunk(2) -> a * gelu(g); weight rows interleaved per 32-wide unit on the host."""
     _setup()
@@ -463,6 +542,18 @@ CASES = {
     "conv2x2_parity_strided_out": case_conv_strided_out,
     "conv3x3_unet8_splitk_b16": lambda: case_conv(N=16, H=8, W=8, Cin=1280, Cout=1280, bias_n=True, f32_out=True, seed=27),
     "conv3x3_unet8_splitk_shortcut": lambda: case_conv(N=16, H=8, W=8, Cin=1280, Cout=1280, x2c=2560, f32_out=True, seed=28),
+    # --- deterministic split-K (epilogue_splitk): 8 / 4 / 3 / 2 slices, every epilogue flavour, ragged tiles
+    "splitk8_8x8_res_f32": lambda: case_conv(N=1, H=8, W=8, Cin=1280, Cout=1280, res="f32", f32_out=True, seed=131),
+    "splitk8_8x8_n2_biasn_bf16": lambda: case_conv(N=2, H=8, W=8, Cin=1280, Cout=1280, bias_n=True, seed=132),
+    "splitk8_ragged_7x9": lambda: case_conv(N=3, H=7, W=9, Cin=1280, Cout=320, res="bf16", seed=133),
+    "splitk4_16x16_both_out": lambda: case_conv(N=2, H=16, W=16, Cin=1280, Cout=1280, res="f32", both_out=True, seed=134),
+    "splitk4_16x16_shortcut_k2560": lambda: case_conv(N=2, H=16, W=16, Cin=1280, Cout=1280, x2c=2560, f32_out=True, seed=135),
+    "splitk2_32x32_bf16": lambda: case_conv(N=1, H=32, W=32, Cin=1280, Cout=640, bias_n=True, seed=136),
+    "splitk_stride2_16x16": lambda: case_conv(N=2, H=32, W=32, Cin=1280, Cout=1280, stride=2, f32_out=True, seed=137),
+    "splitk_invariance_bitwise": case_splitk_invariance,
+    "conv_relu_epilogues": case_conv_relu,
+    "maxpool3x3s2": case_maxpool,
+    "lpips_layer": case_lpips_layer,
     "linear_ff_out_res_f32_bf16out": lambda: case_linear(M=4096, K=1280, N=320, res="f32", seed=26),
     # --- attention
     "attn_self_d40": lambda: case_attention(B=2, heads=8, d=40, Nq=1024),

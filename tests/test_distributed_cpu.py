@@ -18,7 +18,8 @@ def _worker(rank, world, port, n_items, q):
     from image_restoration_and_enhancement_b200 import metrics, sweep
     idx = sweep.shard(n_items, rank, world)
     rng = lambda i: np.random.default_rng(i)
-    vals = {"psnr": [float(rng(i).uniform(5, 40)) for i in idx], "ssim": [float(rng(i + 1000).uniform(0, 1)) for i in idx]}
+    vals = {"psnr": [float(rng(i).uniform(5, 40)) for i in idx], "ssim": [float(rng(i + 1000).uniform(0, 1)) for i in idx],
+            "lpips": [float(rng(i + 2000).uniform(0, 1)) for i in idx]}            # the (psnr, ssim, lpips) triple of north_star
     full = metrics.gather_per_image(idx, vals)
     if rank == 0:
         q.put(metrics.summarize("denoise", full, n_items))
@@ -42,8 +43,10 @@ def test_sharded_gather_is_bit_identical_to_single_process():
         assert p.exitcode == 0
     rng = lambda i: np.random.default_rng(i)
     single = metrics.summarize("denoise", {"psnr": [float(rng(i).uniform(5, 40)) for i in range(n)],
-                                            "ssim": [float(rng(i + 1000).uniform(0, 1)) for i in range(n)]}, n)
-    for k in ("psnr", "ssim"):
+                                            "ssim": [float(rng(i + 1000).uniform(0, 1)) for i in range(n)],
+                                            "lpips": [float(rng(i + 2000).uniform(0, 1)) for i in range(n)]}, n)
+    assert set(got["metrics"]) == {"psnr", "ssim", "lpips"}
+    for k in ("psnr", "ssim", "lpips"):
         for stat in ("mean", "std", "min", "max", "median"):
             assert got["metrics"][k][stat] == single["metrics"][k][stat]        # bit-exact, not approx
 

@@ -28,6 +28,12 @@ def test_clip_text_encoder_parity():
     assert err <= tol, f"CLIP last_hidden_state rel-L2 {err:.3e} > {tol}"
 
 
+def test_lpips_parity():
+    """a15 / f2: LPIPS (AlexNet) on the conv kernel vs the fp32 restatement, same seeded weights; batch-invariant."""
+    err, tol = mc.case_lpips()
+    assert err <= tol, f"LPIPS relative error {err:.3e} > {tol}"
+
+
 def test_vae_encode_parity():
     err, tol = mc.case_vae_encode(1)
     assert err <= tol, f"VAE encoder moments rel-L2 {err:.3e}"
@@ -44,8 +50,13 @@ def test_pipeline_vs_oracle(task):
     r = mc.case_pipeline(task)
     expect_steps = {"denoise": 11, "colorize": 23, "sr": 17, "inpaint": 18}[task]
     assert r["timesteps_match"] and r["steps"] == expect_steps
-    assert max(r["unet_step_rel"]) <= mc.UNET_TOL, r
+    assert len(r["unet_step_rel"]) == expect_steps and max(r["unet_step_rel"]) <= mc.UNET_TOL, r       # every step
     assert r["psnr"] >= mc.PSNR_MIN, r
+    # the state the loop carries: VAE-encoded + noised start, every intermediate latent, the latent handed to the decoder
+    print(f"{task}: init {r['init_latents_rel']:.3e} final {r['final_latents_rel']:.3e} "
+          f"max-step {max(r['latents_rel_per_step']):.3e} psnr {r['psnr']:.2f}")
+    assert r["init_latents_rel"] <= mc.LATENT_TOL and r["final_latents_rel"] <= mc.LATENT_TOL, r
+    assert max(r["latents_rel_per_step"]) <= mc.LATENT_TOL, r
 
 
 def test_batched_call_equals_separate_calls():
