@@ -11,8 +11,10 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-LIB = HERE / "librestoragen.so"
-STAMP = HERE / "build" / "stamp.txt"
+# RG_LIB_OUT=<path>: build an experimental variant (e.g. RG_NVCC_EXTRA=-DRG_GEMM_TUNING) next to the product library
+LIB = Path(os.environ["RG_LIB_OUT"]).resolve() if os.environ.get("RG_LIB_OUT") else HERE / "librestoragen.so"
+OBJDIR = HERE / ("build_alt" if os.environ.get("RG_LIB_OUT") else "build")
+STAMP = OBJDIR / "stamp.txt"
 SOURCES = ["api.cu", "gemm.cu", "attention.cu", "norm.cu", "elementwise.cu", "metrics.cu", "lpips.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("RG_NVCC_EXTRA", "").split()
@@ -40,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return LIB
     nvcc = _nvcc()
-    objdir = HERE / "build"
+    objdir = OBJDIR
     objdir.mkdir(exist_ok=True)
 
     def compile_one(src: str) -> Path:

@@ -23,7 +23,10 @@ int check_launch(const char* kernel) {
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-static std::atomic<int> g_pdl{3};         // bit 0: GEMM / attention / glue kernels, bit 1: norm kernels
+// bit 0: GEMM / attention / glue kernels, bit 1: GroupNorm kernels.  Default 1: measured on the batch-2 UNet evaluation
+// (profiles/r02_floor_*.txt) plain 5.94 ms, mode 3 5.82 ms, mode 1 5.60 ms -- the two-pass GroupNorm gets SLOWER with an
+// early-scheduled dependent (15.5 -> 22.3 us at 2 x 64 x 64 x 320), everything else gains 0.4-1.7 us per launch.
+static std::atomic<int> g_pdl{1};
 bool pdl_enabled(int cls) { return (g_pdl.load(std::memory_order_relaxed) >> cls) & 1; }
 
 int current_device() {

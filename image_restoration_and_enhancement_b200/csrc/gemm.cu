@@ -337,6 +337,23 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
 // No CTA ever waits for another one (the last arriver does the work), so there is no forward-progress hazard.
 constexpr int kMaxSplit = 8;
 
+// sum[j] = partial[0][j] + partial[1][j] + ... in slice order; all KS * 4 loads (L2, bypassing L1) are in flight together
+template <int KS>
+__device__ __forceinline__ void splitk_sum(const float4* src, size_t pitch4, float4 (&sum)[4]) {
+    float4 v[KS][4];
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[s][j] = __ldcg(src + s * pitch4 + j * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float4 a = v[0][j];
+#pragma unroll
+        for (int s = 1; s < KS; ++s) { a.x += v[s][j].x; a.y += v[s][j].y; a.z += v[s][j].z; a.w += v[s][j].w; }
+        sum[j] = a;
+    }
+}
+
 template <int BNC, int EW>
 __device__ __noinline__ void epilogue_splitk(const GemmParams& p, uint8_t* staging, uint64_t* acc_full, uint64_t* acc_empty,
                                              uint32_t tmem_base, uint32_t rank, int cluster_id, int n_clusters, int warp,
@@ -359,27 +376,40 @@ __device__ __noinline__ void epilogue_splitk(const GemmParams& p, uint8_t* stagi
     const bool prim_f32 = p.prim_f32 != 0, prim_store = p.prim_store != 0, sec_store = p.sec_store != 0;
     const bool silu = p.act == 1, relu = p.act == 3, out_f16 = p.out_f16 != 0, res_f32 = p.res_f32 != 0;
     const float scale = p.scale;
+    // `p` lives in the kernel parameter space and is reached through a generic pointer here: every p.xxx is a full
+    // memory round trip (~1 us).  Everything the loops need is read ONCE into registers -- four dependent parameter
+    // loads per unit made the fix-up 25 us long (profiles/r02_splitk_experiments.txt).
+    const int ksplit = p.ksplit, n_tiles_n = p.n_tiles_n, tiles_w = p.tiles_w, tiles_h = p.tiles_h, lw = p.lw;
+    const int pOW = p.OW, pOH = p.OH, pN = p.N, dbg = p.dbg;
+    const long long osn = p.osn, osh = p.osh, osw = p.osw, bias_n_ld = p.bias_n_ld;
+    const float* const bias = p.bias;
+    const float* const bias_n = p.bias_n;
+    const void* const res = p.res;
+    float* const ws_part = p.ws_part;
+    int* const ws_cnt = p.ws_cnt;
+    const CUtensorMap* const pmap = &p.pmap;
+    const CUtensorMap* const hmap = &p.hmap;
     auto pack16 = [&](float lo, float hi) { return out_f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); };
     const size_t slice_pitch = (size_t)2 * EW * REGION;   // floats between slice s and s + 1 of one output tile
     uint32_t cc = 0, A = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++cc) {
-        const int ks = tile % p.ksplit, t2 = tile / p.ksplit;
-        const int mp = t2 / p.n_tiles_n, n_tile = t2 - mp * p.n_tiles_n;
+        const int ks = tile % ksplit, t2 = tile / ksplit;
+        const int mp = t2 / n_tiles_n, n_tile = t2 - mp * n_tiles_n;
         const int m_tile = 2 * mp + (int)rank;
-        const int twi = m_tile % p.tiles_w;
-        const int rest = m_tile / p.tiles_w;
-        const int thi = rest % p.tiles_h, tni = rest / p.tiles_h;
-        const int cw = twi * TW + (row0 & (TW - 1)), ch = thi * TH + ((row0 >> p.lw) & (TH - 1)), cn = tni * TN + (row0 >> lwh);
-        const int ow = twi * TW + (row & (TW - 1)), oh = thi * TH + ((row >> p.lw) & (TH - 1)), n = tni * TN + (row >> lwh);
-        const bool valid = ow < p.OW && oh < p.OH && n < p.N;
+        const int twi = m_tile % tiles_w;
+        const int rest = m_tile / tiles_w;
+        const int thi = rest % tiles_h, tni = rest / tiles_h;
+        const int cw = twi * TW + (row0 & (TW - 1)), ch = thi * TH + ((row0 >> lw) & (TH - 1)), cn = tni * TN + (row0 >> lwh);
+        const int ow = twi * TW + (row & (TW - 1)), oh = thi * TH + ((row >> lw) & (TH - 1)), n = tni * TN + (row >> lwh);
+        const bool valid = ow < pOW && oh < pOH && n < pN;
         const bool any_valid = __any_sync(0xffffffffu, valid);       // all-padding warps (odd last tile, M < 256) skip the dump
         const uint32_t slot = cc % Cfg::SLOTS, use = cc / Cfg::SLOTS;
         mbar_wait(&acc_full[slot], use & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)row0 << 16) + slot * BNC;
-        float* const tile_base = p.ws_part + ((size_t)t2 * p.ksplit * 2 + rank) * EW * REGION + (size_t)ew * REGION;
-        // ---- phase 1: dump this slice's partial units
-        if (any_valid) {
+        float* const tile_base = ws_part + ((size_t)t2 * ksplit * 2 + rank) * EW * REGION + (size_t)ew * REGION;
+        // ---- phase 1: dump this slice's partial units  (dbg bits 8 / 16 / 32: timing experiments, RG_GEMM_TUNING builds only)
+        if (any_valid && !(dbg & 8)) {
             float4* const my = reinterpret_cast<float4*>(tile_base + (size_t)ks * slice_pitch);
 #pragma unroll 1
             for (int k = 0; k < CNT; ++k) {
@@ -395,22 +425,24 @@ __device__ __noinline__ void epilogue_splitk(const GemmParams& p, uint8_t* stagi
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(acc_empty_leader + slot * 8);
-        if (!any_valid) continue;
+        if (!any_valid || (dbg & 16)) continue;
         // ---- publish, elect the last arriver
-        __threadfence();
+        if (!(dbg & 64)) __threadfence();
         __syncwarp();
         int last = 0;
-        if (lane == 0) {
-            int* const c = p.ws_cnt + ((size_t)t2 * 2 + rank) * EW + ew;
-            last = atomicAdd(c, 1) == p.ksplit - 1;
+        if (dbg & 128) {
+            last = ks == ksplit - 1;
+        } else if (lane == 0) {
+            int* const c = ws_cnt + ((size_t)t2 * 2 + rank) * EW + ew;
+            last = atomicAdd(c, 1) == ksplit - 1;
             if (last) atomicExch(c, 0);                    // self-resetting: every slice of this launch has arrived
         }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (!last) continue;
-        __threadfence();
+        if (!(dbg & 256)) __threadfence();
         // ---- phase 2: ordered reduction + the normal epilogue
-        const long long off = valid ? (long long)n * p.osn + (long long)oh * p.osh + (long long)ow * p.osw : 0;
-        const float* const bn_row = p.bias_n ? p.bias_n + (long long)(n < p.N ? n : p.N - 1) * p.bias_n_ld : nullptr;
+        const long long off = valid ? (long long)n * osn + (long long)oh * osh + (long long)ow * osw : 0;
+        const float* const bn_row = bias_n ? bias_n + (long long)(n < pN ? n : pN - 1) * bias_n_ld : nullptr;
         const float4* const part0 = reinterpret_cast<const float4*>(tile_base);
 #pragma unroll 1
         for (int k = 0; k < CNT; ++k, ++A) {
@@ -419,38 +451,35 @@ __device__ __noinline__ void epilogue_splitk(const GemmParams& p, uint8_t* stagi
             uint8_t* const hb = hbuf0 + (A % 2) * 1024;
             if (lane == 0) bulk_wait_read<1>();            // the store issued two units ago has drained these buffers
             __syncwarp();
-            // every partial of the unit is requested before the first one is used (32 independent L2 loads per lane in
-            // flight; a serial load -> add chain cost one L2 round trip per slice and column group), then added in slice
-            // order: fixed, independent of arrival order
-            float4 part[kMaxSplit][4];
-#pragma unroll
-            for (int s2 = 0; s2 < kMaxSplit; ++s2)
-                if (s2 < p.ksplit) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) part[s2][j] = __ldcg(part0 + (size_t)s2 * (slice_pitch / 4) + k * 128 + j * 32 + lane);
-                }
+            // every partial of the unit is requested before the first one is used, then added in slice order (fixed,
+            // independent of arrival order); the slice count is a compile-time constant of splitk_sum (2 / 4 / 8) -- a
+            // run-time count with predicated loads tripled the instruction count of this loop, and one warp per SM
+            // sub-partition executes it alone
+            float4 sum[4];
+            const float4* const src = part0 + k * 128 + lane;
+            if (dbg & 32) splitk_sum<1>(src, slice_pitch / 4, sum);
+            else if (ksplit == 8) splitk_sum<8>(src, slice_pitch / 4, sum);
+            else if (ksplit == 4) splitk_sum<4>(src, slice_pitch / 4, sum);
+            else splitk_sum<2>(src, slice_pitch / 4, sum);
             uint32_t pk[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                float4 a = part[0][j];
-#pragma unroll
-                for (int s2 = 1; s2 < kMaxSplit; ++s2)
-                    if (s2 < p.ksplit) { a.x += part[s2][j].x; a.y += part[s2][j].y; a.z += part[s2][j].z; a.w += part[s2][j].w; }
+                const float4 a = sum[j];
                 float y0 = a.x * scale, y1 = a.y * scale, y2 = a.z * scale, y3 = a.w * scale;
-                if (p.bias) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol + 4 * j));
+                if (bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + gcol + 4 * j));
                     y0 += b.x; y1 += b.y; y2 += b.z; y3 += b.w;
                 }
                 if (bn_row) {
                     const float4 b = __ldg(reinterpret_cast<const float4*>(bn_row + gcol + 4 * j));
                     y0 += b.x; y1 += b.y; y2 += b.z; y3 += b.w;
                 }
-                if (p.res && valid) {
+                if (res && valid) {
                     if (res_f32) {
-                        const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + off + gcol + 4 * j);
+                        const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(res) + off + gcol + 4 * j);
                         y0 += r.x; y1 += r.y; y2 += r.z; y3 += r.w;
                     } else {
-                        const uint2 r2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + off + gcol + 4 * j);
+                        const uint2 r2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(res) + off + gcol + 4 * j);
                         const float2 f0 = unpack_bf16x2(r2.x), f1 = unpack_bf16x2(r2.y);
                         y0 += f0.x; y1 += f0.y; y2 += f1.x; y3 += f1.y;
                     }
@@ -467,9 +496,9 @@ __device__ __noinline__ void epilogue_splitk(const GemmParams& p, uint8_t* stagi
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
-                if (prim_store) tma_store_4d(&p.pmap, pb, gcol, cw, ch, cn);
-                if (sec_store) tma_store_4d(&p.hmap, hb, gcol, cw, ch, cn);
+            if (lane == 0 && !(dbg & 512)) {
+                if (prim_store) tma_store_4d(pmap, pb, gcol, cw, ch, cn);
+                if (sec_store) tma_store_4d(hmap, hb, gcol, cw, ch, cn);
                 bulk_commit();
             }
         }
@@ -990,7 +1019,7 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
             if (c->act == RG_ACT_RELU) mode |= 1 << 20;  // no specialised unit code: run-time-flag epilogue
             if (c->scale != 1.0f) mode |= 256;
             if (c->out16_dtype == RG_DT_F16) mode |= 512;
-            gp.epi_mode = gp.dbg ? (1 << 20) : mode;    // debug experiments run the generic (run-time flag) epilogue
+            gp.epi_mode = (gp.dbg & 7) ? (1 << 20) : mode;    // debug experiments run the generic (run-time flag) epilogue
         }
     }
 
@@ -1006,13 +1035,13 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
     const int clusters = sm_count() / 2;
     // ---- deterministic split-K for the few-pixel levels with a long K (epilogue_splitk).  The slice count is a function
     // of the PER-IMAGE geometry (OH*OW, K) only -- never of N -- so an image's result does not depend on the batch size.
-    if (gp.epi_tma && Cout % 160 == 0 && c->act != RG_ACT_GEGLU && c->splitk_ws && gp.dbg == 0) {
+    if (gp.epi_tma && Cout % 160 == 0 && c->act != RG_ACT_GEGLU && c->splitk_ws && (gp.dbg & 7) == 0) {
         const long long hw = (long long)OH * OW;
         // at most 8 / 4 / 2 slices at the 8x8 / 16x16 / 32x32 levels, at least 12 k-blocks per slice, and only when the
         // main loop is long enough (>= 48 k-blocks) to pay for the dump + fix-up (about 3 us, i.e. ~18 k-blocks of MMA)
         int ks = hw <= 64 ? 8 : hw <= 256 ? 4 : hw <= 1024 ? 2 : 1;
         if (gp.total_kblk < 48) ks = 1;
-        if (ks > gp.total_kblk / 12) ks = gp.total_kblk / 12;
+        while (ks > 1 && ks > gp.total_kblk / 12) ks >>= 1;                          // 8, 4 or 2 (compile-time fix-up loops)
         if (ks > 1) {
             using Cfg = GemmCfg<160, 1, 8>;
             constexpr long long kRegion = (long long)((Cfg::N_TILE / 16 + Cfg::PARTS - 1) / Cfg::PARTS) * 2048;   // bytes per (tile, slice, rank, warp)

@@ -279,13 +279,14 @@ __global__ void __launch_bounds__(512, IN_F32 ? 2 : 1) gn_apply_kernel(const GnP
 // the bf16 result: one launch and one HBM read instead of two launches and two reads.  No inter-block communication at
 // all, so the result is deterministic and independent of the batch size by construction.  An item is 4 consecutive
 // channels of one pixel (16 B fp32 / 8 B bf16); C1 is a multiple of 8, so an item never straddles the two sources.
-// grid = (groups, N), 256 threads, dynamic smem = HW * cpg * sizeof(input element)
-template <bool IN_F32>
-__global__ void __launch_bounds__(256) gn_fused_small_kernel(const GnParams p) {
+// grid = (groups, N), NT threads (256; 512 for slices above 96 KB -- the 64x64 level, one block per SM, so twice the loads
+// in flight), dynamic smem = HW * cpg * sizeof(input element)
+template <bool IN_F32, int NT>
+__global__ void __launch_bounds__(NT) gn_fused_small_kernel(const GnParams p) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ __align__(16) unsigned char s_slice[];
-    __shared__ double s_part[2][8];
+    __shared__ double s_part[2][NT / 32];
     __shared__ float s_stat[2];
     __shared__ float s_scale[128], s_shift[128];
     using Vec = typename std::conditional<IN_F32, float4, uint2>::type;
@@ -309,23 +310,23 @@ __global__ void __launch_bounds__(256) gn_fused_small_kernel(const GnParams p) {
     float s = 0.f, ss = 0.f;
     int it = threadIdx.x;
     constexpr int UF = 8;                             // loads in flight per thread; accumulation stays in item order
-    for (; it < items; it += UF * 256) {
+    for (; it < items; it += UF * NT) {
         Vec v[UF];
 #pragma unroll
         for (int u = 0; u < UF; ++u) {
             if constexpr (IN_F32) v[u] = make_float4(0.f, 0.f, 0.f, 0.f); else v[u] = make_uint2(0u, 0u);
-            if (it + u * 256 < items) v[u] = *src_of(it + u * 256);
+            if (it + u * NT < items) v[u] = *src_of(it + u * NT);
         }
 #pragma unroll
         for (int u = 0; u < UF; ++u) {
-            if (it + u * 256 < items) slice[it + u * 256] = v[u];
+            if (it + u * NT < items) slice[it + u * NT] = v[u];
             float f[4];
             unpack(v[u], f);                          // slots past the end hold +0
 #pragma unroll
             for (int i = 0; i < 4; ++i) { s += f[i]; ss += f[i] * f[i]; }
         }
     }
-    // fixed-order block reduction in fp64: butterfly inside each warp, the 8 warp sums added in warp order
+    // fixed-order block reduction in fp64: butterfly inside each warp, the NT / 32 warp sums added in warp order
     double ds = s, dq = ss;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { ds += __shfl_xor_sync(0xffffffffu, ds, o); dq += __shfl_xor_sync(0xffffffffu, dq, o); }
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(256) gn_fused_small_kernel(const GnParams p) {
     __syncthreads();
     if (threadIdx.x == 0) {
         double sum = 0.0, sq = 0.0;
-        for (int w = 0; w < 8; ++w) { sum += s_part[0][w]; sq += s_part[1][w]; }
+        for (int w = 0; w < NT / 32; ++w) { sum += s_part[0][w]; sq += s_part[1][w]; }
         const double inv_cnt = 1.0 / ((double)p.cpg * (double)p.HW);
         const double m = sum * inv_cnt;
         const double var = fmax(sq * inv_cnt - m * m, 0.0);
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(256) gn_fused_small_kernel(const GnParams p) {
         s_shift[threadIdx.x] = p.beta[cg0 + threadIdx.x] - s_stat[0] * sc;
     }
     __syncthreads();
-    for (it = threadIdx.x; it < items; it += 256) {
+    for (it = threadIdx.x; it < items; it += NT) {
         const int pix = it / ipp, j = (it - pix * ipp) * 4;
         float f[4];
         unpack(slice[it], f);
@@ -362,14 +363,15 @@ __global__ void __launch_bounds__(256) gn_fused_small_kernel(const GnParams p) {
     }
 }
 
-constexpr size_t kGnFusedMaxSmem = 96 * 1024;
+constexpr size_t kGnFusedSmallSmem = 96 * 1024;      // up to here: 256 threads, two blocks per SM
+constexpr size_t kGnFusedMaxSmem = 200 * 1024;       // up to here: 512 threads, one block per SM (64x64 x 320 fp32 = 160 KB)
 // the choice depends on (HW, C, groups, dtype) only -- never on N -- so batch invariance is kept
 static bool gn_use_fused(const rg_gn_t* g) {
     const int C = g->C1 + g->C2;
     if (C % g->groups) return false;
     const int cpg = C / g->groups;
     const size_t isz = g->in_dtype == RG_DT_F32 ? 4 : 2;
-    return g->HW <= 1024 && cpg % 4 == 0 && cpg <= 128 && (size_t)g->HW * cpg * isz <= kGnFusedMaxSmem;
+    return g->HW <= 4096 && cpg % 4 == 0 && cpg <= 128 && (size_t)g->HW * cpg * isz <= kGnFusedMaxSmem;
 }
 
 static int fill_gn(const rg_gn_t* g, GnParams& p, dim3& grid, int& threads) {
@@ -610,13 +612,21 @@ extern "C" int rg_groupnorm(const rg_gn_t* g, rg_stream_t stream) {
         int rc = fill_gn(g, p, grid, threads);
         if (rc) return rc;
         if (!g->y) return set_error(RG_ERR_ARG, "groupnorm: null output");
-        static std::atomic<bool> done_t[kMaxDevices], done_f[kMaxDevices];
-        if ((rc = ensure_smem_attr(reinterpret_cast<const void*>(&gn_fused_small_kernel<true>), (int)kGnFusedMaxSmem, done_t, "cudaFuncSetAttribute(gn_fused_small_kernel)"))) return rc;
-        if ((rc = ensure_smem_attr(reinterpret_cast<const void*>(&gn_fused_small_kernel<false>), (int)kGnFusedMaxSmem, done_f, "cudaFuncSetAttribute(gn_fused_small_kernel)"))) return rc;
+        static std::atomic<bool> done[4][kMaxDevices];
+        const void* fns[4] = {reinterpret_cast<const void*>(&gn_fused_small_kernel<true, 256>), reinterpret_cast<const void*>(&gn_fused_small_kernel<false, 256>),
+                              reinterpret_cast<const void*>(&gn_fused_small_kernel<true, 512>), reinterpret_cast<const void*>(&gn_fused_small_kernel<false, 512>)};
+        for (int i = 0; i < 4; ++i)
+            if ((rc = ensure_smem_attr(fns[i], (int)kGnFusedMaxSmem, done[i], "cudaFuncSetAttribute(gn_fused_small_kernel)"))) return rc;
         const size_t smem = (size_t)p.HW * p.cpg * (p.in_f32 ? 4 : 2);
         const dim3 fgrid((unsigned)p.groups, (unsigned)p.N);
-        if (p.in_f32) launch_kernel<1>(gn_fused_small_kernel<true>, dim3(fgrid), dim3(256), smem, reinterpret_cast<cudaStream_t>(stream), p);
-        else launch_kernel<1>(gn_fused_small_kernel<false>, dim3(fgrid), dim3(256), smem, reinterpret_cast<cudaStream_t>(stream), p);
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        if (smem <= kGnFusedSmallSmem) {
+            if (p.in_f32) launch_kernel<1>(gn_fused_small_kernel<true, 256>, dim3(fgrid), dim3(256), smem, st, p);
+            else launch_kernel<1>(gn_fused_small_kernel<false, 256>, dim3(fgrid), dim3(256), smem, st, p);
+        } else {
+            if (p.in_f32) launch_kernel<1>(gn_fused_small_kernel<true, 512>, dim3(fgrid), dim3(512), smem, st, p);
+            else launch_kernel<1>(gn_fused_small_kernel<false, 512>, dim3(fgrid), dim3(512), smem, st, p);
+        }
         count_launch();
         return check_launch("gn_fused_small_kernel");
     }

@@ -209,16 +209,29 @@ class UNetB200:
         return out
 
     # ------------------------------------------------------------------------------------------ forward
-    def forward(self, latents: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
+    def time_embedding(self, timesteps: torch.Tensor) -> torch.Tensor:
+        """timesteps f32 [M] -> f32 [M, sum of resnet widths]: time_embedding MLP and all 22 ``time_emb_proj(silu(.))`` in
+        three GEMMs.  Depends on the timestep only, so a sampling run computes it for ALL its steps in one go before the
+        loop (rows are independent: the values equal those of a per-step evaluation bit for bit)."""
+        M = timesteps.shape[0]
+        te = ops.timestep_embedding(timesteps, 320)
+        e1, _ = ops.linear(te, self.w_t1, images=M, bias=self.b_t1, act=RG_ACT_SILU, out_bf16=True)
+        e2, _ = ops.linear(e1, self.w_t2, images=M, bias=self.b_t2, act=RG_ACT_SILU, out_bf16=True)     # silu(temb)
+        _, temb_all = ops.linear(e2, self.w_temb, images=M, bias=self.b_temb, out_f32=True)
+        return temb_all
+
+    def forward(self, latents: torch.Tensor, timesteps: torch.Tensor | None = None,
+                temb_all: torch.Tensor | None = None) -> torch.Tensor:
         """latents: f32 channels-last [n_mod, h, w, in_channels] (n_mod divides the context batch: under CFG the same
-        latents feed both halves); timesteps: f32 [Bu].  Returns eps f32 [Bu, h, w, 4]."""
+        latents feed both halves); timesteps: f32 [Bu], or ``temb_all``: the precomputed ``time_embedding`` rows as a
+        [Bu, total] view (row stride 0 when every sample shares the timestep).  Returns eps f32 [Bu, h, w, 4]."""
         Bu = self.ctx_batch
         n_mod, h, w, cin = latents.shape
-        assert cin == self.in_channels and Bu % n_mod == 0 and timesteps.shape[0] == Bu
-        te = ops.timestep_embedding(timesteps, 320)
-        e1, _ = ops.linear(te, self.w_t1, images=Bu, bias=self.b_t1, act=RG_ACT_SILU, out_bf16=True)
-        e2, _ = ops.linear(e1, self.w_t2, images=Bu, bias=self.b_t2, act=RG_ACT_SILU, out_bf16=True)     # silu(temb)
-        _, temb_all = ops.linear(e2, self.w_temb, images=Bu, bias=self.b_temb, out_f32=True)
+        assert cin == self.in_channels and Bu % n_mod == 0
+        if temb_all is None:
+            assert timesteps is not None and timesteps.shape[0] == Bu
+            temb_all = self.time_embedding(timesteps)
+        assert temb_all.shape[0] == Bu and temb_all.stride(1) == 1
 
         cols = ops.im2col_small(latents, Bu, 3, 1, 1, h, w, self.kpad_in)
         _, x = ops.conv2d(cols, self.w_conv_in, bias=self.b_conv_in, out_f32=True)

@@ -584,6 +584,10 @@ CASES = {
     "gn_b16_bf16_tiny": lambda: case_groupnorm(N=16, H=8, W=8, C1=1280, in_f32=False, seed=36),
     "gn_b16_c2560": lambda: case_groupnorm(N=16, H=8, W=8, C1=1280, C2=1280, raw=True, seed=37),
     "gn_batch_invariant_bitwise": case_groupnorm_shapes_agree,
+    # one-pass kernel, 512-thread variant (slice 96..200 KB: the 64x64 level)
+    "gn_64x64_c320_f32_onepass": lambda: case_groupnorm(N=2, H=64, W=64, C1=320, seed=38),
+    "gn_64x64_concat640_bf16_onepass": lambda: case_groupnorm(N=3, H=64, W=64, C1=320, C2=320, in_f32=False, raw=True, seed=39),
+    "gn_32x32_c1280_f32_onepass": lambda: case_groupnorm(N=2, H=32, W=32, C1=640, C2=640, raw=True, seed=40),
     "ln_f32_320": lambda: case_layernorm(),
     "ln_bf16_1280": lambda: case_layernorm(rows=333, C=1280, in_f32=False, seed=42),
     "softmax_rows": lambda: case_softmax_rows(),

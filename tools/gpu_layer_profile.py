@@ -89,8 +89,8 @@ with torch.no_grad():
     # whole-op timings (eager back-to-back and graph replay)
     say()
     say(f"eager UNet eval b{2 * B}: {timed(lambda: unet.forward(lat, ts)):.3f} ms")
-    run = pipe._unet_step_fn(lat, 2 * B)
-    say(f"graph UNet eval b{2 * B}: {timed(lambda: run(500)):.3f} ms")
+    run = pipe._unet_step_fn(lat, 2 * B); trow = unet.time_embedding(torch.full((1,), 500.0, device=dev))
+    say(f"graph UNet eval b{2 * B}: {timed(lambda: run(trow)):.3f} ms")
     say(f"VAE encode b{B}: {timed(lambda: vae.encode_moments(img)):.3f} ms")
     say(f"VAE decode b{B}: {timed(lambda: vae.decode(lat * 0.18215)):.3f} ms")
     task = "colorize" if B > 1 else "denoise"
