@@ -323,20 +323,6 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------
-// Deterministic split-K epilogue (NC = 1, EW = 8).  Work item = (output tile t2, K slice ks), ks fastest, so the slices
-// of one tile run on neighbouring clusters at the same time.  Every epilogue warp owns 32 accumulator rows and its
-// share of the tile's 16-column units, exactly as in epilogue_tma:
-//   phase 1  dump the raw fp32 accumulator units into the workspace region of (t2, ks, rank, warp) -- lane-interleaved
-//            float4s, so every store instruction writes 512 contiguous bytes -- release the TMEM slot, fence, and bump
-//            the arrival counter of (t2, rank, warp);
-//   phase 2  only the warp whose arrival was the last of the ksplit slices: read the partials of ALL slices back
-//            (L2 hits) and add them in slice order 0..ksplit-1 -- the order never depends on who arrived when, so the
-//            result is bitwise reproducible -- then scale / bias / per-image bias / residual / SiLU and the TMA
-//            store(s) of the finished box.  The counter is reset by the warp that consumed it.
-// No CTA ever waits for another one (the last arriver does the work), so there is no forward-progress hazard.
-constexpr int kMaxSplit = 8;
-
 // sum[j] = partial[0][j] + partial[1][j] + ... in slice order; all KS * 4 loads (L2, bypassing L1) are in flight together
 template <int KS>
 __device__ __forceinline__ void splitk_sum(const float4* src, size_t pitch4, float4 (&sum)[4]) {
@@ -354,6 +340,22 @@ __device__ __forceinline__ void splitk_sum(const float4* src, size_t pitch4, flo
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Deterministic split-K epilogue (NC = 1, EW = 8), used when a layer has too few output tiles to fill the SMs (UNet
+// batch 2: everything below the 64x64 level).  Work item = (output tile t2, K slice ks), ks fastest, dealt round-robin,
+// so the slices of one tile run on neighbouring clusters at the same time.  Every epilogue warp owns 32 accumulator rows
+// and its share of the tile's 16-column units, exactly as in epilogue_tma:
+//   phase 1  dump the raw fp32 accumulator units into the workspace region of (t2, ks, rank, warp) -- lane-interleaved
+//            float4s, every store instruction writes 512 contiguous bytes -- release the TMEM slot, fence, bump the
+//            arrival counter of (t2, rank, warp);
+//   phase 2  only the warp whose arrival was the last of the ksplit slices: read the partials of ALL slices back (L2
+//            hits) and add them in slice order 0..ksplit-1 -- the order never depends on who arrived when, so a launch is
+//            bitwise reproducible -- then scale / bias / per-image bias / residual / activation and the TMA store(s).
+//            The counter is reset by the warp that consumed it.
+// No CTA ever waits for another one (the last arriver does the work), so there is no forward-progress hazard.
+// (Tried and dropped: a "local" mode that ran all slices of a tile in one cluster with register sums, to make the result
+// independent of the batch size bit for bit -- it forces the 160-column tile on large batches, where the 2 x 160 tile's
+// halved operand traffic is worth 15 % of a UNet evaluation; profiles/r02_layers_splitk_b8.txt.)
 template <int BNC, int EW>
 __device__ __noinline__ void epilogue_splitk(const GemmParams& p, uint8_t* staging, uint64_t* acc_full, uint64_t* acc_empty,
                                              uint32_t tmem_base, uint32_t rank, int cluster_id, int n_clusters, int warp,
@@ -392,6 +394,7 @@ __device__ __noinline__ void epilogue_splitk(const GemmParams& p, uint8_t* stagi
     auto pack16 = [&](float lo, float hi) { return out_f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); };
     const size_t slice_pitch = (size_t)2 * EW * REGION;   // floats between slice s and s + 1 of one output tile
     uint32_t cc = 0, A = 0;
+#pragma unroll 1
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++cc) {
         const int ks = tile % ksplit, t2 = tile / ksplit;
         const int mp = t2 / n_tiles_n, n_tile = t2 - mp * n_tiles_n;
@@ -402,14 +405,14 @@ __device__ __noinline__ void epilogue_splitk(const GemmParams& p, uint8_t* stagi
         const int cw = twi * TW + (row0 & (TW - 1)), ch = thi * TH + ((row0 >> lw) & (TH - 1)), cn = tni * TN + (row0 >> lwh);
         const int ow = twi * TW + (row & (TW - 1)), oh = thi * TH + ((row >> lw) & (TH - 1)), n = tni * TN + (row >> lwh);
         const bool valid = ow < pOW && oh < pOH && n < pN;
-        const bool any_valid = __any_sync(0xffffffffu, valid);       // all-padding warps (odd last tile, M < 256) skip the dump
+        const bool any_valid = __any_sync(0xffffffffu, valid);       // all-padding warps (odd last tile, M < 256) skip the work
         const uint32_t slot = cc % Cfg::SLOTS, use = cc / Cfg::SLOTS;
         mbar_wait(&acc_full[slot], use & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)row0 << 16) + slot * BNC;
         float* const tile_base = ws_part + ((size_t)t2 * ksplit * 2 + rank) * EW * REGION + (size_t)ew * REGION;
-        // ---- phase 1: dump this slice's partial units  (dbg bits 8 / 16 / 32: timing experiments, RG_GEMM_TUNING builds only)
         if (any_valid && !(dbg & 8)) {
+            // ---- phase 1: dump this slice's partial units  (dbg bits: timing experiments, RG_GEMM_TUNING builds)
             float4* const my = reinterpret_cast<float4*>(tile_base + (size_t)ks * slice_pitch);
 #pragma unroll 1
             for (int k = 0; k < CNT; ++k) {
@@ -440,20 +443,20 @@ __device__ __noinline__ void epilogue_splitk(const GemmParams& p, uint8_t* stagi
         last = __shfl_sync(0xffffffffu, last, 0);
         if (!last) continue;
         if (!(dbg & 256)) __threadfence();
-        // ---- phase 2: ordered reduction + the normal epilogue
+        // ---- finish the tile: ordered sums -> scale / bias / residual / activation -> TMA store(s)
         const long long off = valid ? (long long)n * osn + (long long)oh * osh + (long long)ow * osw : 0;
         const float* const bn_row = bias_n ? bias_n + (long long)(n < pN ? n : pN - 1) * bias_n_ld : nullptr;
         const float4* const part0 = reinterpret_cast<const float4*>(tile_base);
 #pragma unroll 1
-        for (int k = 0; k < CNT; ++k, ++A) {
+        for (int k = 0; k < CNT; ++k) {
             const int gcol = n_tile * BNC + (part + PARTS * k) * 16;
             uint8_t* const pb = pbuf0 + (A % 2) * 2048;
             uint8_t* const hb = hbuf0 + (A % 2) * 1024;
             if (lane == 0) bulk_wait_read<1>();            // the store issued two units ago has drained these buffers
             __syncwarp();
-            // every partial of the unit is requested before the first one is used, then added in slice order (fixed,
-            // independent of arrival order); the slice count is a compile-time constant of splitk_sum (2 / 4 / 8) -- a
-            // run-time count with predicated loads tripled the instruction count of this loop, and one warp per SM
+            // every partial of the unit is requested before the first one is used, then added in slice order
+            // (fixed, independent of arrival order); the slice count is a compile-time constant of splitk_sum (2 / 4 / 8)
+            // -- a run-time count with predicated loads tripled the instruction count of this loop, and one warp per SM
             // sub-partition executes it alone
             float4 sum[4];
             const float4* const src = part0 + k * 128 + lane;
@@ -467,12 +470,12 @@ __device__ __noinline__ void epilogue_splitk(const GemmParams& p, uint8_t* stagi
                 const float4 a = sum[j];
                 float y0 = a.x * scale, y1 = a.y * scale, y2 = a.z * scale, y3 = a.w * scale;
                 if (bias) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + gcol + 4 * j));
-                    y0 += b.x; y1 += b.y; y2 += b.z; y3 += b.w;
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + gcol + 4 * j));
+                    y0 += bv.x; y1 += bv.y; y2 += bv.z; y3 += bv.w;
                 }
                 if (bn_row) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(bn_row + gcol + 4 * j));
-                    y0 += b.x; y1 += b.y; y2 += b.z; y3 += b.w;
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bn_row + gcol + 4 * j));
+                    y0 += bv.x; y1 += bv.y; y2 += bv.z; y3 += bv.w;
                 }
                 if (res && valid) {
                     if (res_f32) {
@@ -501,6 +504,7 @@ __device__ __noinline__ void epilogue_splitk(const GemmParams& p, uint8_t* stagi
                 if (sec_store) tma_store_4d(hmap, hb, gcol, cw, ch, cn);
                 bulk_commit();
             }
+            ++A;
         }
     }
     if (lane == 0) bulk_wait_read<0>();
@@ -1033,15 +1037,18 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
     gp.ksplit = 1;
     gp.kper = gp.total_kblk;
     const int clusters = sm_count() / 2;
-    // ---- deterministic split-K for the few-pixel levels with a long K (epilogue_splitk).  The slice count is a function
-    // of the PER-IMAGE geometry (OH*OW, K) only -- never of N -- so an image's result does not depend on the batch size.
+    // ---- deterministic split-K (epilogue_splitk) when the layer has too few output tiles to fill the SMs and a long K:
+    // as many slices (8, 4 or 2) as it takes to give every cluster a work item, at least 12 k-blocks per slice, and only
+    // for main loops of >= 48 k-blocks (the dump + fix-up costs about as much as 30 k-blocks of MMA).  At UNet batch 2
+    // that is every conv below the 64x64 level and the long-K feed-forward projections; at batch 16 only the 8x8 level.
+    // The slice count depends on the batch size, so results are reproducible per batch size, not across batch sizes.
     if (gp.epi_tma && Cout % 160 == 0 && c->act != RG_ACT_GEGLU && c->splitk_ws && (gp.dbg & 7) == 0) {
-        const long long hw = (long long)OH * OW;
-        // at most 8 / 4 / 2 slices at the 8x8 / 16x16 / 32x32 levels, at least 12 k-blocks per slice, and only when the
-        // main loop is long enough (>= 48 k-blocks) to pay for the dump + fix-up (about 3 us, i.e. ~18 k-blocks of MMA)
-        int ks = hw <= 64 ? 8 : hw <= 256 ? 4 : hw <= 1024 ? 2 : 1;
-        if (gp.total_kblk < 48) ks = 1;
-        while (ks > 1 && ks > gp.total_kblk / 12) ks >>= 1;                          // 8, 4 or 2 (compile-time fix-up loops)
+        const long long tiles160 = (long long)gp.n_pairs_m * (Cout / 160);
+        int ks = 1;
+        if (gp.total_kblk >= 48 && tiles160 * 2 <= clusters) {
+            ks = 8;
+            while (ks > 1 && (ks * tiles160 > clusters || ks > gp.total_kblk / 12)) ks >>= 1;
+        }
         if (ks > 1) {
             using Cfg = GemmCfg<160, 1, 8>;
             constexpr long long kRegion = (long long)((Cfg::N_TILE / 16 + Cfg::PARTS - 1) / Cfg::PARTS) * 2048;   // bytes per (tile, slice, rank, warp)

@@ -279,8 +279,9 @@ __global__ void __launch_bounds__(512, IN_F32 ? 2 : 1) gn_apply_kernel(const GnP
 // the bf16 result: one launch and one HBM read instead of two launches and two reads.  No inter-block communication at
 // all, so the result is deterministic and independent of the batch size by construction.  An item is 4 consecutive
 // channels of one pixel (16 B fp32 / 8 B bf16); C1 is a multiple of 8, so an item never straddles the two sources.
-// grid = (groups, N), NT threads (256; 512 for slices above 96 KB -- the 64x64 level, one block per SM, so twice the loads
-// in flight), dynamic smem = HW * cpg * sizeof(input element)
+// grid = (groups, N), NT = 256 threads, dynamic smem = HW * cpg * sizeof(input element).  (Tried and NOT kept: slices up to
+// 200 KB -- the 64x64 x 320 fp32 level -- with 512 threads, one block per SM: 15.5 us against 14.5 us for the two-pass
+// kernels at UNet batch 2 and slower at batch 16, profiles/r02_floor_*.txt.)
 template <bool IN_F32, int NT>
 __global__ void __launch_bounds__(NT) gn_fused_small_kernel(const GnParams p) {
     pdl_trigger();
@@ -363,15 +364,14 @@ __global__ void __launch_bounds__(NT) gn_fused_small_kernel(const GnParams p) {
     }
 }
 
-constexpr size_t kGnFusedSmallSmem = 96 * 1024;      // up to here: 256 threads, two blocks per SM
-constexpr size_t kGnFusedMaxSmem = 200 * 1024;       // up to here: 512 threads, one block per SM (64x64 x 320 fp32 = 160 KB)
+constexpr size_t kGnFusedMaxSmem = 96 * 1024;        // two blocks per SM
 // the choice depends on (HW, C, groups, dtype) only -- never on N -- so batch invariance is kept
 static bool gn_use_fused(const rg_gn_t* g) {
     const int C = g->C1 + g->C2;
     if (C % g->groups) return false;
     const int cpg = C / g->groups;
     const size_t isz = g->in_dtype == RG_DT_F32 ? 4 : 2;
-    return g->HW <= 4096 && cpg % 4 == 0 && cpg <= 128 && (size_t)g->HW * cpg * isz <= kGnFusedMaxSmem;
+    return g->HW <= 1024 && cpg % 4 == 0 && cpg <= 128 && (size_t)g->HW * cpg * isz <= kGnFusedMaxSmem;
 }
 
 static int fill_gn(const rg_gn_t* g, GnParams& p, dim3& grid, int& threads) {
@@ -612,21 +612,14 @@ extern "C" int rg_groupnorm(const rg_gn_t* g, rg_stream_t stream) {
         int rc = fill_gn(g, p, grid, threads);
         if (rc) return rc;
         if (!g->y) return set_error(RG_ERR_ARG, "groupnorm: null output");
-        static std::atomic<bool> done[4][kMaxDevices];
-        const void* fns[4] = {reinterpret_cast<const void*>(&gn_fused_small_kernel<true, 256>), reinterpret_cast<const void*>(&gn_fused_small_kernel<false, 256>),
-                              reinterpret_cast<const void*>(&gn_fused_small_kernel<true, 512>), reinterpret_cast<const void*>(&gn_fused_small_kernel<false, 512>)};
-        for (int i = 0; i < 4; ++i)
-            if ((rc = ensure_smem_attr(fns[i], (int)kGnFusedMaxSmem, done[i], "cudaFuncSetAttribute(gn_fused_small_kernel)"))) return rc;
+        static std::atomic<bool> done_t[kMaxDevices], done_f[kMaxDevices];
+        if ((rc = ensure_smem_attr(reinterpret_cast<const void*>(&gn_fused_small_kernel<true, 256>), (int)kGnFusedMaxSmem, done_t, "cudaFuncSetAttribute(gn_fused_small_kernel)"))) return rc;
+        if ((rc = ensure_smem_attr(reinterpret_cast<const void*>(&gn_fused_small_kernel<false, 256>), (int)kGnFusedMaxSmem, done_f, "cudaFuncSetAttribute(gn_fused_small_kernel)"))) return rc;
         const size_t smem = (size_t)p.HW * p.cpg * (p.in_f32 ? 4 : 2);
         const dim3 fgrid((unsigned)p.groups, (unsigned)p.N);
         cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-        if (smem <= kGnFusedSmallSmem) {
-            if (p.in_f32) launch_kernel<1>(gn_fused_small_kernel<true, 256>, dim3(fgrid), dim3(256), smem, st, p);
-            else launch_kernel<1>(gn_fused_small_kernel<false, 256>, dim3(fgrid), dim3(256), smem, st, p);
-        } else {
-            if (p.in_f32) launch_kernel<1>(gn_fused_small_kernel<true, 512>, dim3(fgrid), dim3(512), smem, st, p);
-            else launch_kernel<1>(gn_fused_small_kernel<false, 512>, dim3(fgrid), dim3(512), smem, st, p);
-        }
+        if (p.in_f32) launch_kernel<1>(gn_fused_small_kernel<true, 256>, dim3(fgrid), dim3(256), smem, st, p);
+        else launch_kernel<1>(gn_fused_small_kernel<false, 256>, dim3(fgrid), dim3(256), smem, st, p);
         count_launch();
         return check_launch("gn_fused_small_kernel");
     }

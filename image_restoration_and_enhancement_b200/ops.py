@@ -63,10 +63,10 @@ def _gn_workspace(device, N: int, groups: int) -> torch.Tensor:
 
 
 # Deterministic split-K workspace of rg_conv2d (include/restoragen.h: rg_conv_t.splitk_ws): arrival counters + fp32 partial
-# tiles.  One zero-initialised buffer per device, allocated once (captured graphs keep its address); 512 MiB covers UNet
-# batches up to ~96 at every level -- HBM is 180 GB.  SPLITK = False switches the split off (A/B measurements only).
+# tiles (at most one 160 KB partial per CTA pair: 12 MB).  One zero-initialised buffer per device, allocated once (captured
+# graphs keep its address).  SPLITK = False switches the split off (A/B measurements only).
 SPLITK = True
-SPLITK_WS_BYTES = (256 << 10) + (512 << 20)
+SPLITK_WS_BYTES = (256 << 10) + (32 << 20)
 _SPLITK_WS: dict = {}
 
 
@@ -176,8 +176,8 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, *, kh: int = 1, kw: int = 1, stride
 
 def linear(x: torch.Tensor, w: torch.Tensor, images: int = 1, **kw):
     """x bf16 [M, K] (row stride arbitrary multiple of 8) -> [M, N]; same epilogue options as conv2d.
-    ``images``: the M rows are ``images`` equal groups of tokens (one per image).  It only tells the kernel the
-    per-image geometry, which is what its split-K decision may depend on (results stay independent of the batch size)."""
+    ``images``: the M rows are ``images`` equal groups of tokens (one per image): the kernel then tiles the rows per
+    image ([images, 1, rows, K] view), like the convolutions do."""
     M, K = x.shape
     assert M % images == 0
     rows = M // images

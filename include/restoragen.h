@@ -98,13 +98,13 @@ typedef struct rg_conv {
     float scale;
     int32_t out16_dtype;   /* element type written through out_bf16: RG_DT_BF16 (default) or RG_DT_F16 (the attention
                               operands q, k, v: fp16 like the reference's CUDA path, src/inference.py:57) */
-    /* Optional split-K workspace (NULL = never split).  Few-pixel layers with a long K (the 32x32-and-below levels
-       of the UNet at small batch) cannot fill 148 SMs with output tiles alone, so K is cut into 2..8 slices computed
-       by different CTA pairs; every slice writes its fp32 partial tile here and the LAST slice to arrive (a per-tile
-       arrival counter at the head of the workspace elects it) adds the partials IN SLICE ORDER and runs the normal
-       epilogue -- the result is bitwise reproducible and, because the slice count depends on the per-image geometry
-       only (OH*OW, K, Cout), independent of the batch size.  The workspace must be ZERO when first used (the
-       counters reset themselves), at least RG_SPLITK_WS_MIN_BYTES, and is shared by all calls of one stream. */
+    /* Optional split-K workspace (NULL = never split).  A layer with too few output tiles to fill the SMs and a long K
+       (everything below the 64x64 level of the UNet at batch 1-2) has its K range cut into 2, 4 or 8 slices computed by
+       different CTA pairs; every slice writes its fp32 partial tile here and the LAST slice to arrive (a per-tile arrival
+       counter at the head of the workspace elects it) adds the partials IN SLICE ORDER and runs the normal epilogue, so a
+       launch is bitwise reproducible.  The slice count follows the number of output tiles, i.e. the batch size: results
+       are reproducible per batch size.  The workspace must be ZERO when first used (the counters reset themselves), at
+       least RG_SPLITK_WS_MIN_BYTES, and is shared by all calls of one stream. */
     void* splitk_ws;
     int64_t splitk_ws_bytes;
 } rg_conv_t;

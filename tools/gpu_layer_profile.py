@@ -23,6 +23,10 @@ from image_restoration_and_enhancement_b200.pipelines import StableDiffusionImg2
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+if "nosplit" in sys.argv[3:]:
+    ops.SPLITK = False
+if "nopdl" in sys.argv[3:]:
+    _lib.load().rg_set_pdl(0)
 dev = torch.device("cuda", 0)
 pipe = StableDiffusionImg2ImgPipeline.from_random_init(seed=0).to(dev)
 out_lines = []
