@@ -257,7 +257,7 @@ def build_runner(c: dict, dev, rank: int, pipes: dict):
     B = c["batch"]
     if c["kind"] not in pipes:
         cls = StableDiffusionInpaintPipeline if c["kind"] == "inpaint" else StableDiffusionImg2ImgPipeline
-        pipes[c["kind"]] = cls.from_random_init(seed=0 if c["kind"] == "img2img" else 1000).to(dev)
+        pipes[c["kind"]] = cls.from_random_init(seed=0 if c["kind"] == "img2img" else 1000, device=str(dev)).to(dev)
     pipe = pipes[c["kind"]]
     # every rank works on its own slice of the (synthetic) image stream: weak scaling, no data-path collective
     data = synth.batch(c["task"], range(rank * B, (rank + 1) * B))

@@ -68,6 +68,7 @@ class RestorationPipeline:
         self.device = ("cuda" if torch.cuda.is_available() else "cpu") if device == "auto" else device
         self.dtype = torch.bfloat16 if self.device == "cuda" else torch.float32
         self.models: dict[str, object] = {}
+        self._shared: dict[tuple, object] = {}
         self.seed = seed
         self.backend = backend
         self.strict = strict
@@ -89,7 +90,7 @@ class RestorationPipeline:
         if self.device != "cuda":
             raise RuntimeError("the Stable Diffusion path needs a CUDA (sm_100a) device; there is no CPU path")
         if random_init is not None:
-            pipe = pipe_class.from_random_init(seed=int(random_init))
+            pipe = pipe_class.from_random_init(seed=int(random_init), device="cuda")
         else:
             try:
                 pipe = pipe_class.from_pretrained(model_path, torch_dtype=self.dtype, use_safetensors=True)
@@ -104,10 +105,15 @@ class RestorationPipeline:
 
     def _load_sd(self, task: str, pipe_class):
         """Resolution order of the reference loaders (``:199-455``): fine-tuned dir if it exists, the
-        ``pretrained_id`` when ``fine_tuned_dir == "nonexistent"``, otherwise FileNotFoundError."""
+        ``pretrained_id`` when ``fine_tuned_dir == "nonexistent"``, otherwise FileNotFoundError.
+        Tasks whose weights come from the same source (same class and random-init seed) share ONE pipeline object -- and
+        with it the device weights and the captured UNet graph: the sweep's three 4-channel tasks pay one cold start."""
         cfg = self.config[task]
         if cfg.get("random_init") is not None:
-            return self._load_sd_pipeline(pipe_class, "", _TASK_NAMES[task], random_init=cfg["random_init"])
+            key = (pipe_class.__name__, "random_init", int(cfg["random_init"]))
+            if key not in self._shared:
+                self._shared[key] = self._load_sd_pipeline(pipe_class, "", _TASK_NAMES[task], random_init=cfg["random_init"])
+            return self._shared[key]
         ft = Path(cfg["fine_tuned_dir"])
         pretrained_mode = cfg["fine_tuned_dir"] == "nonexistent"
         if ft.exists():

@@ -70,6 +70,25 @@ SPLITK_WS_BYTES = (256 << 10) + (32 << 20)
 _SPLITK_WS: dict = {}
 
 
+class splitk:
+    """``with ops.splitk(False):`` -- run (and capture) GEMMs without the K split.  The split follows the number of output
+    tiles, i.e. the batch size, so results are reproducible per batch size; with it off every kernel of the library is
+    batch-invariant bit for bit (what the sharded sweep's bookkeeping contract needs)."""
+
+    def __init__(self, enabled: bool):
+        self.enabled = enabled
+
+    def __enter__(self):
+        global SPLITK
+        self.prev, SPLITK = SPLITK, self.enabled
+        return self
+
+    def __exit__(self, *exc):
+        global SPLITK
+        SPLITK = self.prev
+        return False
+
+
 def _splitk_workspace(device) -> torch.Tensor:
     key = (device.type, device.index)
     ws = _SPLITK_WS.get(key)

@@ -182,13 +182,19 @@ def run_sweep(n_images: int = 100, tasks=TASKS, size: int = 512, seed: int = 42,
         from .lpips import LPIPSB200, random_lpips_state_dict
         lp = LPIPSB200(random_lpips_state_dict(lpips_seed), device=f"cuda:{torch.cuda.current_device()}")
     results = {}
-    for task in tasks:
-        idx, vals, secs = run_task(pipe, task, n_images, rank, world, size, handoff_mode=handoff_mode,
-                                   metrics_backend=metrics_backend, workdir=workdir, lpips_model=lp)
-        full = metrics.gather_per_image(idx, vals)
-        if rank == 0:
-            results[task] = metrics.summarize(task, full, n_images)
-            results[task]["seconds_rank0"] = secs
+    from . import ops
+    # The sweep's contract is that the statistics do not depend on how the images were sharded (1 process or 8, ragged last
+    # batches): every kernel is batch-invariant bit for bit except the K split of the few-tile GEMMs, which follows the
+    # batch size -- so the sweep samples without it (it only matters below batch 4; cost at batch 8: ~1 %).
+    with ops.splitk(False):
+        for task in tasks:
+            idx, vals, secs = run_task(pipe, task, n_images, rank, world, size, handoff_mode=handoff_mode,
+                                       metrics_backend=metrics_backend, workdir=workdir, lpips_model=lp)
+            full = metrics.gather_per_image(idx, vals)
+            if rank == 0:
+                results[task] = metrics.summarize(task, full, n_images)
+                results[task]["seconds_rank0"] = secs
+                results[task]["images_per_s_wall"] = n_images / secs if secs > 0 else None
     return results if rank == 0 else None
 
 
@@ -198,9 +204,12 @@ if __name__ == "__main__":
     if "RANK" in os.environ:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
         dist.init_process_group("nccl")
+    t_all = time.time()
     res = run_sweep(n_images=int(os.environ.get("SWEEP_IMAGES", "16")), handoff_mode=os.environ.get("SWEEP_HANDOFF", "memory"),
                     metrics_backend=os.environ.get("SWEEP_METRICS", "gpu"), workdir=os.environ.get("SWEEP_WORKDIR"))
     if res is not None:
+        res["_wall_seconds_incl_model_setup"] = time.time() - t_all
+        res["_world_size"] = dist.get_world_size() if dist.is_initialized() else 1
         print(json.dumps(res, default=float))
     if dist.is_initialized():
         dist.destroy_process_group()

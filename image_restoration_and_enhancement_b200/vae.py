@@ -56,13 +56,14 @@ class VAEB200:
                 raise KeyError(f"VAE state dict is missing {k}")
             if tuple(state_dict[k].shape) != tuple(s):
                 raise ValueError(f"{k}: shape {tuple(state_dict[k].shape)} != {s}")
-        sd, dev = state_dict, device
+        dev = device
+        sd = {k: state_dict[k].to(dev, non_blocking=True) for k in shapes}      # repack on the device (see unet.py)
         self.device = dev
         f = lambda k: sd[k].to(dev, f32).contiguous()
         boc = (128, 256, 512, 512)
         # ---- encoder
-        w = torch.zeros((boc[0], 64), dtype=f32)
-        w[:, :27] = pack_conv(sd["encoder.conv_in.weight"].to("cpu", f32))
+        w = torch.zeros((boc[0], 64), dtype=f32, device=dev)
+        w[:, :27] = pack_conv(sd["encoder.conv_in.weight"].to(f32))
         self.e_in = (w.to(dev, bf16).contiguous(), f("encoder.conv_in.bias"))
         self.e_down = []
         for i in range(4):
@@ -79,8 +80,8 @@ class VAEB200:
         self.quant = (sd["quant_conv.weight"].flatten(1).to(dev, f32).contiguous(), f("quant_conv.bias"))
         # ---- decoder
         self.post_quant = (sd["post_quant_conv.weight"].flatten(1).to(dev, f32).contiguous(), f("post_quant_conv.bias"))
-        w = torch.zeros((512, 64), dtype=f32)
-        w[:, :36] = pack_conv(sd["decoder.conv_in.weight"].to("cpu", f32))
+        w = torch.zeros((512, 64), dtype=f32, device=dev)
+        w[:, :36] = pack_conv(sd["decoder.conv_in.weight"].to(f32))
         self.d_in = (w.to(dev, bf16).contiguous(), f("decoder.conv_in.bias"))
         self.d_mid = (_VResnet(sd, "decoder.mid_block.resnets.0.", dev), _VAttn(sd, "decoder.mid_block.attentions.0.", dev),
                       _VResnet(sd, "decoder.mid_block.resnets.1.", dev))
