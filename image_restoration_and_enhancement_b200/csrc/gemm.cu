@@ -185,6 +185,7 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
     uint32_t cc = 0;
     int cw = 0, ch = 0, cn = 0, n_tile = 0, tni = 0;
     if (cluster_id < total_tiles) box_origin(cluster_id, cw, ch, cn, n_tile, tni);
+    pdl_wait();                                           // first global access below (residual prefetch, bias, stores)
     if (has_res && lane == 0 && CNT > 0 && cluster_id < total_tiles && !skip_units) {      // very first residual box
         mbar_expect_tx(&res_bar[0], res_bytes);
         tma_load_4d(pbuf0, &p.resmap, &res_bar[0], (n_tile * Cfg::N_TILE + part * UW) >> gsh, cw, ch, cn);
@@ -362,7 +363,7 @@ __device__ __noinline__ void epilogue_splitk(const GemmParams& p, uint8_t* stagi
                                              int lane) {
     using Cfg = GemmCfg<BNC, 1, EW>;
     constexpr int NBUF = Cfg::NBUF, HBUF = Cfg::HBUF, PARTS = Cfg::PARTS;
-    static_assert(NBUF >= 2 && HBUF >= 2, "split-K epilogue rotates two store buffers");
+    static_assert(NBUF >= 2, "split-K epilogue rotates two primary store buffers");
     constexpr int UPC = BNC / 16;                         // 16-column units per tile
     constexpr int CNT_MAX = (UPC + PARTS - 1) / PARTS;    // units per warp (region pitch)
     constexpr int REGION = CNT_MAX * 512;                 // floats per (tile, slice, rank, warp)
@@ -394,6 +395,7 @@ __device__ __noinline__ void epilogue_splitk(const GemmParams& p, uint8_t* stagi
     auto pack16 = [&](float lo, float hi) { return out_f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); };
     const size_t slice_pitch = (size_t)2 * EW * REGION;   // floats between slice s and s + 1 of one output tile
     uint32_t cc = 0, A = 0;
+    pdl_wait();                                           // parameters are in registers; global memory from here on
 #pragma unroll 1
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++cc) {
         const int ks = tile % ksplit, t2 = tile / ksplit;
@@ -451,8 +453,10 @@ __device__ __noinline__ void epilogue_splitk(const GemmParams& p, uint8_t* stagi
         for (int k = 0; k < CNT; ++k) {
             const int gcol = n_tile * BNC + (part + PARTS * k) * 16;
             uint8_t* const pb = pbuf0 + (A % 2) * 2048;
-            uint8_t* const hb = hbuf0 + (A % 2) * 1024;
-            if (lane == 0) bulk_wait_read<1>();            // the store issued two units ago has drained these buffers
+            uint8_t* const hb = hbuf0 + (A % HBUF) * 1024;
+            if (lane == 0) {                               // the store that last used these buffers has drained them
+                if (HBUF >= 2 || !sec_store) bulk_wait_read<1>(); else bulk_wait_read<0>();
+            }
             __syncwarp();
             // every partial of the unit is requested before the first one is used, then added in slice order
             // (fixed, independent of arrival order); the slice count is a compile-time constant of splitk_sum (2 / 4 / 8)
@@ -548,7 +552,9 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     cluster_sync_all();                 // barriers of BOTH CTAs are initialised before anyone signals across the pair
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
-    pdl_wait();                         // everything above overlapped the previous kernel; from here on its results are needed
+    // Everything above overlapped the previous kernel (programmatic dependent launch).  Each role calls pdl_wait() itself,
+    // right before ITS first access to global memory: the producer before its first TMA load, the epilogue warps after
+    // their parameter reads and geometry set-up; the MMA warp only touches shared and tensor memory and never waits.
 
     // work items: (pair of 128-pixel tiles, column tile, K split); the K split is the fastest index
     const int total_tiles = p.n_pairs_m * p.n_tiles_n * p.ksplit;
@@ -557,6 +563,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     if (warp == 0) {
         // ===================================================================== TMA producer (both CTAs)
         if (lane == 0) {
+            pdl_wait();
             int stage = 0; uint32_t phase = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
                 const int ks = tile % p.ksplit, t2 = tile / p.ksplit;
@@ -630,7 +637,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     } else {
         // ===================================================================== epilogue (both CTAs, own 128 rows)
         if (p.ksplit > 1) {
-            if constexpr (NC == 1 && EW == 8)
+            if constexpr (NC == 1)
                 epilogue_splitk<BNC, EW>(p, staging, acc_full, acc_empty, tmem_base, rank, cluster_id, n_clusters, warp, lane);
         } else if (p.epi_tma) {
 #define RG_EPI_CASE(M) case (M): epilogue_tma<BNC, NC, EW, (M)>(p, staging, acc_full, acc_empty, res_bar, tmem_base, rank, cluster_id, n_clusters, warp, lane); break;
@@ -660,6 +667,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
             const bool geglu = p.act == 2;
             const uint32_t acc_empty_leader = mapa_shared(smem_u32(acc_empty), 0);
             uint32_t cc = 0;
+            pdl_wait();
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, cc += NC) {
                 const int mp = tile / p.n_tiles_n, n_tile = tile - mp * p.n_tiles_n;
                 const int m_tile = 2 * mp + (int)rank;
@@ -1050,11 +1058,13 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
             while (ks > 1 && (ks * tiles160 > clusters || ks > gp.total_kblk / 12)) ks >>= 1;
         }
         if (ks > 1) {
-            using Cfg = GemmCfg<160, 1, 8>;
+            // 16 epilogue warps: 2-3 units per warp instead of 5 -- the fix-up of a tile is a serial chain of units in the
+            // last-arriving warp (one L2 round trip each), so its depth is what the launch waits for
+            using Cfg = GemmCfg<160, 1, 16>;
             constexpr long long kRegion = (long long)((Cfg::N_TILE / 16 + Cfg::PARTS - 1) / Cfg::PARTS) * 2048;   // bytes per (tile, slice, rank, warp)
             const long long out_tiles = (long long)gp.n_pairs_m * (Cout / 160);
-            const long long cnt_bytes = out_tiles * 2 * 8 * (long long)sizeof(int);
-            const long long part_bytes = out_tiles * ks * 2 * 8 * kRegion;
+            const long long cnt_bytes = out_tiles * 2 * 16 * (long long)sizeof(int);
+            const long long part_bytes = out_tiles * ks * 2 * 16 * kRegion;
             if ((reinterpret_cast<uintptr_t>(c->splitk_ws) & 15) == 0 && cnt_bytes <= RG_SPLITK_COUNTER_BYTES &&
                 RG_SPLITK_COUNTER_BYTES + part_bytes <= c->splitk_ws_bytes) {
                 gp.ksplit = ks;
@@ -1064,7 +1074,7 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
                 } else {
                     gp.ws_cnt = reinterpret_cast<int*>(c->splitk_ws);
                     gp.ws_part = reinterpret_cast<float*>(reinterpret_cast<char*>(c->splitk_ws) + RG_SPLITK_COUNTER_BYTES);
-                    return launch_gemm<160, 1>(gp, c->w, ktot, w_ld, stream);
+                    return launch_gemm<160, 1, 16>(gp, c->w, ktot, w_ld, stream);
                 }
             }
         }
