@@ -46,6 +46,12 @@ elif which == "gn":          # GroupNorm+SiLU: UNet 64x64x320 fp32 (stats + appl
         ops.groupnorm(x, g[:320].contiguous(), bta[:320].contiguous(), silu=True)
         ops.groupnorm(xv, g[:128].contiguous(), bta[:128].contiguous(), eps=1e-6, silu=True)
         ops.groupnorm(xs, g, bta, silu=True)
+elif which == "conv_b2":     # config 1 (UNet batch 2): resnet conv 320->320 3x3 at 64x64, M=8192, N=320, K=2880 (15.1 GFLOP)
+    x = torch.randn((2, 64, 64, 320), device="cuda").to(torch.bfloat16)
+    w = (torch.randn((320, 2880), device="cuda") / 53.0).to(torch.bfloat16)
+    b = torch.randn((320,), device="cuda")
+    for _ in range(4):
+        ops.conv2d(x, w, kh=3, kw=3, pad_t=1, pad_l=1, bias=b, out_bf16=True)
 elif which == "splitk8":     # config-1 shape: 8x8-level resnet conv at UNet batch 2, M=128, N=1280, K=11520 -> 8 K slices
     x = torch.randn((2, 8, 8, 1280), device="cuda").to(torch.bfloat16)
     w = (torch.randn((1280, 11520), device="cuda") / 107.0).to(torch.bfloat16)
