@@ -280,8 +280,9 @@ __global__ void __launch_bounds__(512, IN_F32 ? 2 : 1) gn_apply_kernel(const GnP
 // all, so the result is deterministic and independent of the batch size by construction.  An item is 4 consecutive
 // channels of one pixel (16 B fp32 / 8 B bf16); C1 is a multiple of 8, so an item never straddles the two sources.
 // grid = (groups, N), NT = 256 threads, dynamic smem = HW * cpg * sizeof(input element).  (Tried and NOT kept: slices up to
-// 200 KB -- the 64x64 x 320 fp32 level -- with 512 threads, one block per SM: 15.5 us against 14.5 us for the two-pass
-// kernels at UNet batch 2 and slower at batch 16, profiles/r02_floor_*.txt.)
+// 200 KB with 512 threads, one block per SM -- the VAE's 64x64 x 512 bf16 level took 65.6 us against 33.2 us for the
+// two-pass kernels at 8 images, profiles/r02_gn_onepass_experiment.txt; the UNet's 64x64 x 320 level has 10 channels per
+// group, which the 4-channel items of this kernel do not tile, so it stays two-pass either way.)
 template <bool IN_F32, int NT>
 __global__ void __launch_bounds__(NT) gn_fused_small_kernel(const GnParams p) {
     pdl_trigger();

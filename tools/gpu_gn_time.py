@@ -34,7 +34,8 @@ def say(s):
 SHAPES = [  # N, HW, C, fp32 input
     (16, 4096, 320, True), (16, 4096, 320, False), (16, 4096, 640, True), (16, 1024, 640, True), (16, 1024, 640, False),
     (16, 1024, 1920, True), (16, 256, 1280, True), (16, 256, 1280, False), (16, 256, 2560, True), (16, 64, 1280, True), (16, 64, 2560, True),
-    (8, 262144, 128, False), (8, 65536, 256, False), (8, 16384, 512, False), (8, 4096, 512, False), (1, 4096, 320, True)]
+    (8, 262144, 128, False), (8, 65536, 256, False), (8, 16384, 512, False), (8, 4096, 512, False), (1, 4096, 320, True),
+    (2, 4096, 320, True), (2, 4096, 320, False), (2, 1024, 640, True), (1, 262144, 128, False), (1, 65536, 256, False)]
 say(f"library: {_lib.LIB_PATH.name}")
 say(f"{'shape':34s} {'stats us':>9s} {'GB/s':>7s} {'apply us':>9s} {'GB/s':>7s} {'both us':>8s} {'GB/s':>7s}")
 for N, HW, Cc, f32in in SHAPES:
@@ -44,7 +45,7 @@ for N, HW, Cc, f32in in SHAPES:
     xs = [torch.randn((N, HW, Cc), device=dev, dtype=torch.float32 if f32in else torch.bfloat16) for _ in range(nbuf)]
     y = torch.empty((N, HW, Cc), device=dev, dtype=torch.bfloat16)
     gamma, beta = torch.ones(Cc, device=dev), torch.zeros(Cc, device=dev)
-    ws = ops._gn_workspace(dev, ops.GN_MAX_IMAGES + N * 32 * 2 + N * ops.GN_MAX_BLOCKS * 32 * 2)
+    ws = ops._gn_workspace(dev, N, 32)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def params(x):
@@ -72,7 +73,7 @@ for N, HW, Cc, f32in in SHAPES:
     t_s = timed(lambda p: _lib.check(lib.rg_groupnorm_stats(C.byref(p), st)))
     t_a = timed(lambda p: _lib.check(lib.rg_groupnorm_apply(C.byref(p), st)))
     both = getattr(lib, "rg_groupnorm", None)
-    if both is not None and not os.environ.get("RG_LIB"):
+    if both is not None:
         t_b = timed(lambda p: _lib.check(lib.rg_groupnorm(C.byref(p), st)))          # one-pass kernel where it applies
     else:
         t_b = timed(lambda p: (_lib.check(lib.rg_groupnorm_stats(C.byref(p), st)), _lib.check(lib.rg_groupnorm_apply(C.byref(p), st))))
