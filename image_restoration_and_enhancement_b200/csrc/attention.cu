@@ -7,8 +7,20 @@
 //   warps 0..3   softmax warpgroup of query tile 0   (thread r owns query row r = TMEM lane r: no shuffles)
 //   warps 4..7   softmax warpgroup of query tile 1
 //   warp  8      TMA producer: Q tiles once per item, K/V tiles through a STAGES-deep ring
-//   warp  9      tcgen05.mma issuer:  S_t = Q_t K^T  (M=128, N=BKV, K=d)   -> TMEM columns of S_t
+//   warp  9, 11  tcgen05.mma issuers, ONE THREAD each, one per query tile t (a single thread serves both tiles for the short launches,
+//                AttnParams::n_issuers):
+//                                     S_t = Q_t K^T  (M=128, N=BKV, K=d)   -> TMEM columns of S_t
 //                                     O_t += P_t V   (M=128, N=DV,  K=BKV) -> TMEM columns of O_t
+//   warp  10     fp16 only: writes the ones column into every freshly landed V tile (see below) and only then
+//                publishes the stage to the issuers
+//
+// Why two issuers and a patch warp (round 2): with one issuing warp the period of a 256-query x 128-key step was bound
+// by that warp alone -- tcgen05.mma issue blocks while the pipe's short queue is full (1218 cycles per step), and in
+// between the same thread did five barrier round trips, commits, warp syncs and the 400-cycle ones-column patch, during
+// which the tensor pipe idled (3285 cycles per step with the exponentials compiled out).  Both
+// warpgroups then waited for the same thread at the same point, ran their exponentials in lock-step and left the MUFU
+// pipe idle during their bookkeeping.  Now each warpgroup has its own issuing thread that never syncs a warp, and the
+// patch runs ahead of both in a warp of its own, inside the K/V ring's slack.
 //
 // S is double-buffered per query tile (SBUF = 2): S_t(j+1) is computed while the warpgroup is still busy with
 // S_t(j), so the softmax threads never wait for the tensor core and the MUFU (exp) pipe is the only limiter.
@@ -25,6 +37,7 @@
 // Head dims that are not a multiple of 64 (40, 80, 160 in SD-1.5) are handled by the TMA engine: the tensor
 // map's innermost extent is d, so the rest of each 64-wide box is zero-filled in shared memory.
 // V is consumed directly as an MN-major B operand -- no transpose anywhere.
+#include <stdlib.h>
 #include "common.cuh"
 #include "internal.h"
 
@@ -38,6 +51,8 @@ struct AttnParams {
     int heads, n_qpairs, n_items;
     float scale_log2;     // scale * log2(e)
     long long* trace;     // debug only (rg_debug_attn_trace): per-tile clock64 stamps of CTA 0, else nullptr
+    int n_issuers;        // 1: warp 9 issues for both query tiles; 2: warp 9 -> tile 0, warp 11 -> tile 1
+    int skew;             // cycles by which tile 1 starts behind tile 0 at a CTA's first work item (2 issuers only)
 };
 
 constexpr int kTraceTiles = 64, kTraceStamps = 8;
@@ -72,9 +87,9 @@ struct AttnCfg {
     static constexpr int P_STRIDE = PSEP ? BKV / 2 : 0;
     static constexpr int O_COL = P_COL + 2 * P_STRIDE;
     static constexpr int TMEM_COLS = 512;
-    static constexpr int NBAR = 2 + 4 * SBUF + 4 + 2 * STAGES;
+    static constexpr int NBAR = 2 + 4 * SBUF + 4 + 3 * STAGES;
     static_assert(O_COL + 2 * O_STRIDE <= 512, "TMEM budget");
-    static_assert(NBAR * 8 + 8 <= 256, "barrier area");
+    static_assert(NBAR * 8 + 8 + 16 <= 256, "barrier area");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(BKV == 64 || BKV == 128, "BKV");
     static_assert(SBUF == 1 || SBUF == 2, "SBUF");
@@ -82,7 +97,17 @@ struct AttnCfg {
     static_assert(!PSEP || STAGES >= SBUF + 1, "SBUF tiles of score look-ahead need SBUF+1 K/V stages");
 };
 
-constexpr int kAttnThreads = 320;
+constexpr int kAttnThreads = 384;
+// Stagger (cycles) of query tile 1 behind tile 0 for the long key loops: the two warps that share an SM sub-partition
+// then run their exponential phase (MUFU-bound) and their bookkeeping (barrier round trips, tcgen05.ld / st, row max:
+// issue- and latency-bound, MUFU idle) in anti-phase instead of in lock-step.  About half a step period.
+constexpr int kAttnSkewCycles = 1300;
+#ifndef RG_ATTN_PSTREAM
+#define RG_ATTN_PSTREAM 1
+#endif
+// P_t in its own TMEM columns (PSEP): wait for the previous P V before the exponentials and stream every finished 32-key
+// chunk of P out during them, instead of waiting and storing all of P after the last exponential
+constexpr bool kAttnPStream = RG_ATTN_PSTREAM != 0;
 constexpr float kLazyRescale = 8.0f;       // raise the running max only when a tile exceeds it by > 2^8
 
 // All barrier phases are indexed by the CTA-global key-tile counter G = (items done) * n_kv + j, which is also the
@@ -101,7 +126,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     uint64_t* p_full = s_free + 2 * SBUF;              // [t]       P_t(G) stored, O_t rescaled     (softmax -> tensor core)
     uint64_t* pv_done = p_full + 2;                    // [t]       O_t += P_t(G) V retired         (tensor core -> softmax)
     uint64_t* kv_full = pv_done + 2; uint64_t* kv_empty = kv_full + STAGES;
-    uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(kv_empty + STAGES);
+    uint64_t* kv_land = kv_empty + STAGES;             // [stage]   fp16: TMA bytes landed (-> patch warp -> kv_full)
+    uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(kv_land + STAGES);
+    volatile long long* t0_stamp = reinterpret_cast<volatile long long*>(kv_land + STAGES + 1);   // [item parity] clock64 of warpgroup 0's start
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kv = (p.Nk + BKV - 1) / BKV;
@@ -109,10 +136,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     pdl_trigger();
     if (warp == 8 && lane == 0) { tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap); }
     if (warp == 9 && lane == 0) {
-        mbar_init(&q_full, 1); mbar_init(&q_empty, 1);
+        mbar_init(&q_full, 1); mbar_init(&q_empty, p.n_issuers);
         for (int i = 0; i < 2 * SBUF; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128); }
         for (int t = 0; t < 2; ++t) { mbar_init(&p_full[t], 128); mbar_init(&pv_done[t], 1); }
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], p.n_issuers); mbar_init(&kv_land[s], 1); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&tmem_base_smem, Cfg::TMEM_COLS);
@@ -143,19 +170,47 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                     mbar_wait(&kv_empty[stage], phase ^ 1);
                     uint8_t* sk = sKV + stage * Cfg::STAGE_BYTES;
                     uint8_t* sv = sk + Cfg::K_BYTES;
-                    mbar_expect_tx(&kv_full[stage], Cfg::STAGE_BYTES);
+                    uint64_t* const land = F16 ? &kv_land[stage] : &kv_full[stage];     // fp16: the patch warp publishes kv_full
+                    mbar_expect_tx(land, Cfg::STAGE_BYTES);
 #pragma unroll
                     for (int a = 0; a < DKA; ++a) {
-                        tma_load_4d(sk + a * Cfg::KV_ATOM_BYTES, &p.kmap, &kv_full[stage], a * 64, h, j * BKV, b);
-                        tma_load_4d(sv + a * Cfg::KV_ATOM_BYTES, &p.vmap, &kv_full[stage], a * 64, h, j * BKV, b);
+                        tma_load_4d(sk + a * Cfg::KV_ATOM_BYTES, &p.kmap, land, a * 64, h, j * BKV, b);
+                        tma_load_4d(sv + a * Cfg::KV_ATOM_BYTES, &p.vmap, land, a * 64, h, j * BKV, b);
                     }
                 }
             }
         }
-    } else if (warp == 9) {
-        // ===================================================================== MMA issuer (lane 0 issues; the whole
-        // warp waits on the barriers and, for fp16, patches the ones column into each freshly landed V tile)
-        {
+    } else if (warp == 10) {
+        // ===================================================================== fp16: ones-column patch warp
+        // V[k][d] = 1 for every key row k, so that O_t[:, d] = sum_k P (the softmax denominator) comes out of the P V GEMM.
+        // Column d sits in the TMA zero padding (atom d / 64, 16-byte chunk (d % 64) / 8 of the 128-byte row, SWIZZLE_128B:
+        // chunk ^= row & 7).  TMA rewrites the padding with zeros on every load, so every landed tile is patched, then
+        // handed to the issuers: generic-proxy stores -> fence.proxy.async -> mbarrier arrive -> their tcgen05.mma reads.
+        if constexpr (F16) {
+            uint32_t g = 0;
+            const int chunk = (p.d & 63) >> 3;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                for (int j = 0; j < n_kv; ++j, ++g) {
+                    const uint32_t stage = g % STAGES;
+                    mbar_wait(&kv_land[stage], (g / STAGES) & 1);
+                    uint8_t* sv = sKV + stage * Cfg::STAGE_BYTES + Cfg::K_BYTES + (p.d >> 6) * Cfg::KV_ATOM_BYTES;
+                    for (int k = lane; k < BKV; k += 32)
+                        *reinterpret_cast<uint16_t*>(sv + k * 128 + ((chunk ^ (k & 7)) << 4)) = 0x3C00;   // fp16 1.0
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&kv_full[stage]);
+                }
+            }
+        }
+    } else if (warp == 9 || warp == 11) {
+        // ===================================================================== MMA issuers: one thread per query tile
+        // (warp 9 -> t = 0, warp 11 -> t = 1; with p.n_issuers == 1 warp 9 serves both tiles in turn and warp 11 idles).
+        // The two threads never talk to each other: each waits for the barriers of its own tile, writes its own TMEM
+        // columns, and the barriers they share (q_empty, kv_empty) simply expect one commit from each.
+        const bool two = p.n_issuers == 2;
+        const int t_lo = two ? (warp == 9 ? 0 : 1) : 0;
+        const int t_hi = two ? t_lo + 1 : 2;
+        if (lane == 0 && (two || warp == 9)) {
             // kind::f16 operand format: bits [7,10) A, [10,13) B: 0 = fp16, 1 = bf16
             constexpr uint32_t fmt_clear = F16 ? ~((7u << 7) | (7u << 10)) : ~0u;
             constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0) & fmt_clear;    // Q (K-major smem) x K (K-major smem)
@@ -164,16 +219,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
             const uint32_t skv = smem_u32(sKV);
             auto wait_kv = [&](uint32_t G) {
                 mbar_wait(&kv_full[G % STAGES], (G / STAGES) & 1);
-                if constexpr (F16) {
-                    // V[k][d] = 1 for every key row k: column d sits in the TMA zero padding (atom d / 64, 16-byte chunk
-                    // (d % 64) / 8 of the 128-byte row, SWIZZLE_128B: chunk ^= row & 7)
-                    uint8_t* sv = sKV + (G % STAGES) * Cfg::STAGE_BYTES + Cfg::K_BYTES + (p.d >> 6) * Cfg::KV_ATOM_BYTES;
-                    const int chunk = (p.d & 63) >> 3;
-                    for (int k = lane; k < BKV; k += 32)
-                        *reinterpret_cast<uint16_t*>(sv + k * 128 + ((chunk ^ (k & 7)) << 4)) = 0x3C00;   // fp16 1.0
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                }
                 tc_fence_after();
             };
             // S_t(G) = Q_t K_G^T
@@ -184,16 +229,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                     tc_fence_after();
                 }
                 const uint32_t sk = skv + (G % STAGES) * Cfg::STAGE_BYTES;
-                if (lane == 0) {
 #pragma unroll
-                    for (int ks = 0; ks < DQK / 16; ++ks) {      // columns >= d are zero in both operands
-                        const uint64_t adesc = umma_desc_kmajor_sw128(sq + t * Cfg::Q_TILE_BYTES + (ks / 4) * 128 * 128 + (ks % 4) * 32);
-                        const uint64_t bdesc = umma_desc_kmajor_sw128(sk + (ks / 4) * Cfg::KV_ATOM_BYTES + (ks % 4) * 32);
-                        umma_bf16(tmem_base + (t * SBUF + buf) * BKV, adesc, bdesc, idesc_s, ks != 0 ? 1u : 0u);
-                    }
-                    umma_commit(&s_full[t * SBUF + buf]);
+                for (int ks = 0; ks < DQK / 16; ++ks) {          // columns >= d are zero in both operands
+                    const uint64_t adesc = umma_desc_kmajor_sw128(sq + t * Cfg::Q_TILE_BYTES + (ks / 4) * 128 * 128 + (ks % 4) * 32);
+                    const uint64_t bdesc = umma_desc_kmajor_sw128(sk + (ks / 4) * Cfg::KV_ATOM_BYTES + (ks % 4) * 32);
+                    umma_bf16(tmem_base + (t * SBUF + buf) * BKV, adesc, bdesc, idesc_s, ks != 0 ? 1u : 0u);
                 }
-                __syncwarp();
+                umma_commit(&s_full[t * SBUF + buf]);
             };
             // O_t (+)= P_t(G) V_G
             auto issue_pv = [&](int t, uint32_t G, uint32_t acc) {
@@ -201,57 +243,64 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                 tc_fence_after();
                 const uint32_t sv = skv + (G % STAGES) * Cfg::STAGE_BYTES + Cfg::K_BYTES;
                 const uint32_t p_tmem = PSEP ? tmem_base + Cfg::P_COL + t * Cfg::P_STRIDE : tmem_base + t * BKV;
-                if (lane == 0) {
 #pragma unroll
-                    for (int ks = 0; ks < BKV / 16; ++ks) {
-                        // 16 kv rows per k-step = 2 groups of 8 rows (1024 B each); 64-wide d blocks are KV_ATOM_BYTES apart
-                        const uint64_t bdesc = umma_desc_mnmajor_sw128(sv + ks * 2048, Cfg::KV_ATOM_BYTES, 1024);
-                        // P: two 16-bit values per 32-bit TMEM column -> 16 keys = 8 columns
-                        umma_bf16_ts(tmem_base + Cfg::O_COL + t * Cfg::O_STRIDE, p_tmem + ks * 8, bdesc, idesc_o,
-                                     (acc | (uint32_t)ks) != 0 ? 1u : 0u);
-                    }
-                    umma_commit(&pv_done[t]);
+                for (int ks = 0; ks < BKV / 16; ++ks) {
+                    // 16 kv rows per k-step = 2 groups of 8 rows (1024 B each); 64-wide d blocks are KV_ATOM_BYTES apart
+                    const uint64_t bdesc = umma_desc_mnmajor_sw128(sv + ks * 2048, Cfg::KV_ATOM_BYTES, 1024);
+                    // P: two 16-bit values per 32-bit TMEM column -> 16 keys = 8 columns
+                    umma_bf16_ts(tmem_base + Cfg::O_COL + t * Cfg::O_STRIDE, p_tmem + ks * 8, bdesc, idesc_o,
+                                 (acc | (uint32_t)ks) != 0 ? 1u : 0u);
                 }
-                __syncwarp();
+                umma_commit(&pv_done[t]);
             };
-            auto commit = [&](uint64_t* bar) { if (lane == 0) umma_commit(bar); __syncwarp(); };
+            // tile 1's issuer holds the first score GEMM of every work item back until p.skew cycles after warpgroup 0 has
+            // picked up ITS first score tile (warp 0 stamps clock64 before its s_free arrival; the barrier is only polled
+            // here, warpgroup 0's own issuer consumes it): warpgroup 1 then runs that far behind warpgroup 0 through the
+            // item's key loop, whatever happened at the item boundary
+            auto stagger = [&](uint32_t g0_, uint32_t it_) {
+                if (PSEP && two && t_lo == 1 && p.skew > 0) {          // (s_free / t0_stamp exist for separate P columns only)
+                    mbar_wait(&s_free[g0_ % SBUF], (g0_ / SBUF) & 1);      // warpgroup 0 has started the item's first tile ...
+                    const long long target = t0_stamp[it_ & 1] + (long long)p.skew;   // ... at this time (same SM, same counter)
+                    while (clock64() < target) { }
+                }
+            };
             uint32_t g0 = 0, it = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it, g0 += n_kv) {
                 mbar_wait(&q_full, it & 1);
                 tc_fence_after();
                 if constexpr (!PSEP) {
                     wait_kv(g0);
-                    issue_s(0, g0); issue_s(1, g0);
-                    if (n_kv == 1) commit(&q_empty);
+                    stagger(g0, it);
+                    for (int t = t_lo; t < t_hi; ++t) issue_s(t, g0);
+                    if (n_kv == 1) umma_commit(&q_empty);
                     for (int j = 0; j < n_kv; ++j) {
                         const uint32_t G = g0 + j;
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) {
+                        for (int t = t_lo; t < t_hi; ++t) {
                             issue_pv(t, G, j > 0 ? 1u : 0u);
-                            if (t == 1) commit(&kv_empty[G % STAGES]);   // K_G / V_G consumed once these retire
-                            if (j + 1 < n_kv) {                               // in order behind P_t(G) V: P aliases S_t
-                                if (t == 0) wait_kv(G + 1);
+                            if (t == t_hi - 1) umma_commit(&kv_empty[G % STAGES]);    // K_G / V_G consumed once these retire
+                            if (j + 1 < n_kv) {                                        // in order behind P_t(G) V: P aliases S_t
+                                if (t == t_lo) wait_kv(G + 1);
                                 issue_s(t, G + 1);
-                                if (t == 1 && j + 2 == n_kv) commit(&q_empty);
+                                if (t == t_hi - 1 && j + 2 == n_kv) umma_commit(&q_empty);
                             }
                         }
                     }
                 } else {
                     for (int j = 0; j < SBUF && j < n_kv; ++j) {              // SBUF score tiles of look-ahead
                         wait_kv(g0 + j);
-                        issue_s(0, g0 + j); issue_s(1, g0 + j);
-                        if (j + 1 == n_kv) commit(&q_empty);
+                        if (j == 0) stagger(g0, it);
+                        for (int t = t_lo; t < t_hi; ++t) issue_s(t, g0 + j);
+                        if (j + 1 == n_kv) umma_commit(&q_empty);
                     }
                     for (int j = 0; j < n_kv; ++j) {
                         const uint32_t G = g0 + j;
                         if (j + SBUF < n_kv) {
                             wait_kv(G + SBUF);
-                            issue_s(0, G + SBUF); issue_s(1, G + SBUF);
-                            if (j + SBUF + 1 == n_kv) commit(&q_empty);
+                            for (int t = t_lo; t < t_hi; ++t) issue_s(t, G + SBUF);
+                            if (j + SBUF + 1 == n_kv) umma_commit(&q_empty);
                         }
-                        issue_pv(0, G, j > 0 ? 1u : 0u);
-                        issue_pv(1, G, j > 0 ? 1u : 0u);
-                        commit(&kv_empty[G % STAGES]);
+                        for (int t = t_lo; t < t_hi; ++t) issue_pv(t, G, j > 0 ? 1u : 0u);
+                        umma_commit(&kv_empty[G % STAGES]);
                     }
                 }
             }
@@ -265,8 +314,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         const uint32_t p_tmem0 = tmem_base + lane_addr + Cfg::P_COL + t * Cfg::P_STRIDE;
         const uint32_t o_tmem = tmem_base + lane_addr + Cfg::O_COL + t * Cfg::O_STRIDE;
         const float sl = p.scale_log2;
-        uint32_t g0 = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, g0 += n_kv) {
+        uint32_t g0 = 0, it_s = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, g0 += n_kv, ++it_s) {
             const int qp = item % p.n_qpairs, bh = item / p.n_qpairs;
             const int h = bh % p.heads, b = bh / p.heads;
             float m_run = -INFINITY, l_run = 0.f;
@@ -289,6 +338,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                 }
                 RG_STAMP(2);
                 if constexpr (PSEP) {                            // the buffer can take S_t(G+SBUF) now
+                    if (j == 0 && warp == 0 && lane == 0) t0_stamp[it_s & 1] = clock64();      // see stagger() in the issuer
                     tc_fence_before();
                     mbar_arrive(&s_free[t * SBUF + buf]);
                 }
@@ -340,6 +390,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                     }
                 }
                 RG_STAMP(3);
+                if constexpr (PSEP && kAttnPStream) {            // P_t's own columns: free once O_t += P_t(G-1) V has retired,
+                    if (!quiescent) { mbar_wait(&pv_done[t], (G - 1) & 1); tc_fence_after(); quiescent = true; }   // long ago by now
+                }
                 const float neg_m = -m_run;
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
                 uint32_t pk[BKV / 2];
@@ -351,7 +404,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                         uint32_t h;
                         asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
                         asm("ex2.approx.f16x2 %0, %1;" : "=r"(pk[i / 2]) : "r"(h));
-                        if (!PSEP && (i & 31) == 30)             // aliased: stream each finished 32-key chunk out
+                        if ((!PSEP || kAttnPStream) && (i & 31) == 30)             // stream each finished 32-key chunk out
                             tmem_st16(p_tmem + (i - 30) / 2, reinterpret_cast<uint32_t (&)[16]>(pk[(i - 30) / 2]));
                     }
                 } else {
@@ -364,16 +417,18 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                         l0 += e0; l1 += e1; l2 += e2; l3 += e3;
                         pk[i / 2] = pack_bf16x2(e0, e1);
                         pk[i / 2 + 1] = pack_bf16x2(e2, e3);
-                        if (!PSEP && (i & 31) == 28)             // aliased: stream each finished 32-key chunk out
+                        if ((!PSEP || kAttnPStream) && (i & 31) == 28)             // stream each finished 32-key chunk out
                             tmem_st16(p_tmem + (i - 28) / 2, reinterpret_cast<uint32_t (&)[16]>(pk[(i - 28) / 2]));
                     }
                 }
                 RG_STAMP(4);
-                if constexpr (PSEP) {
+                if constexpr (PSEP && !kAttnPStream) {
                     if (!quiescent) { mbar_wait(&pv_done[t], (G - 1) & 1); tc_fence_after(); }
                     RG_STAMP(5);
 #pragma unroll
                     for (int c = 0; c < BKV / 2; c += 16) tmem_st16(p_tmem + c, reinterpret_cast<uint32_t (&)[16]>(pk[c]));
+                } else {
+                    RG_STAMP(5);
                 }
                 l_run += (l0 + l1) + (l2 + l3);
                 tmem_st_wait();
@@ -457,6 +512,14 @@ static int launch_attn(const rg_attn_t* a, cudaStream_t stream) {
     p.n_items = (int)items;
     p.scale_log2 = a->scale * 1.4426950408889634f;
     p.trace = g_attn_trace;
+    // long key loops: one issuer per warpgroup and the warpgroups half a period apart; short ones (cross attention, the
+    // few-token levels) are latency-bound chains where a second issuer only adds contention (profiles/r02_attn_variants.txt)
+    p.n_issuers = (PSEP && (a->Nk + BKV - 1) / BKV >= 8) ? 2 : 1;
+    p.skew = p.n_issuers == 2 ? kAttnSkewCycles : 0;
+#ifdef RG_ATTN_TUNING            /* perf experiments only: never in the product build */
+    { const char* e = getenv("RG_ATTN_ISSUERS"); if (e) p.n_issuers = atoi(e) == 2 ? 2 : 1; }
+    { const char* e = getenv("RG_ATTN_SKEW"); if (e) p.skew = p.n_issuers == 2 ? atoi(e) : 0; }
+#endif
     const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
     launch_kernel(attention_kernel<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16, CAUSAL>, dim3(grid), dim3(kAttnThreads), Cfg::SMEM_BYTES, stream, p);
     count_launch();

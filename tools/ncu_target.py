@@ -37,6 +37,10 @@ elif which == "attn":        # self-attention at 64x64 latents: B=16, 8 heads, d
     qkv = torch.randn((16, 4096, 3, 8, 40), device="cuda").to(torch.bfloat16)
     for _ in range(3):
         ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], 40 ** -0.5)
+elif which == "attn16":      # the UNet's path: fp16 operands, 2 issuers, staggered warpgroups
+    qkv = torch.randn((16, 4096, 3, 8, 40), device="cuda").half()
+    for _ in range(3):
+        ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], 40 ** -0.5)
 elif which == "gn":          # GroupNorm+SiLU: UNet 64x64x320 fp32 (stats + apply), VAE 512x512x128 bf16, UNet 16x16x1280 (one pass)
     g = torch.ones(1280, device="cuda"); bta = torch.zeros(1280, device="cuda")
     x = torch.randn((16, 64, 64, 320), device="cuda")
