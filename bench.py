@@ -16,7 +16,9 @@ briefly and reported under "extra".
   roofline   the dominant kernel (conv_gemm_kernel, tcgen05 implicit GEMM): algorithmic FLOPs of every launch of one
              UNet evaluation at this config's UNet batch / CUDA-event time of those launches, against the measured
              BURST bf16 peak of MEASURED_PEAKS.json (sustained as the secondary figure), plus per-class fractions
-             (3x3 convs, short-K linears, attention against the tensor peak; GroupNorm / LayerNorm against HBM)
+             (3x3 convs, short-K linears, attention against the tensor peak; GroupNorm / LayerNorm against HBM).
+             The headline config runs the UNet at batch 2 (launch- and fill-bound: 64 CTA-pair tiles at best); the same
+             block at UNet batch 16 is under extra.colorize.roofline
   library_baseline   the same sampling run through torch's library kernels (cuDNN / cuBLASLt / SDPA) on the SAME
              GPU: the oracle module tree in fp16 (the reference's CUDA dtype, src/inference.py:57) and in bf16 with
              channels_last + cudnn.benchmark -- "the kernels to beat on the same box" 
@@ -359,6 +361,10 @@ def run_b200(args, c: dict) -> int:
                                "e2e": cx["batch"] / (mse / 1e3), "unit": UNIT, "batch": cx["batch"],
                                "unet_evals_per_step": cx["unet_evals"],
                                "achieved_tflops_whole_step": cx["tflop_per_img"] * cx["batch"] / (msd / 1e3)}
+                if name == "colorize":
+                    # kernel quality at a batch that fills the machine (UNet batch 16): the same per-launch measurement
+                    # as the headline's roofline block, comparable with round 1's line
+                    extra[name]["roofline"] = kernel_rooflines(px, dev, cx)
             except Exception as e:  # noqa: BLE001
                 extra[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0 and world == 1:

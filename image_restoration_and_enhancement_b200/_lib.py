@@ -8,8 +8,17 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "librestoragen.so"
+# RESTORAGEN_OPERAND_DTYPE=fp16 selects the fp16 parity build (same sources, -DRG_OPERAND_F16): every 16-bit activation and
+# weight is fp16 and the tensor cores multiply fp16 operands, like the reference on CUDA (src/inference.py:57).  The
+# choice is per process and made at import; the host modules allocate their 16-bit tensors as OPERAND_DTYPE_NAME.
+OPERAND_DTYPE_NAME = {"": "bfloat16", "bf16": "bfloat16", "bfloat16": "bfloat16", "fp16": "float16", "f16": "float16",
+                      "float16": "float16"}.get(os.environ.get("RESTORAGEN_OPERAND_DTYPE", "").lower())
+if OPERAND_DTYPE_NAME is None:
+    raise ValueError("RESTORAGEN_OPERAND_DTYPE must be bf16 or fp16")
+LIB_PATH = _HERE / ("librestoragen_f16.so" if OPERAND_DTYPE_NAME == "float16" else "librestoragen.so")
 
 RG_ACT_NONE, RG_ACT_SILU, RG_ACT_GEGLU, RG_ACT_RELU = 0, 1, 2, 3
 RG_DT_BF16, RG_DT_F32, RG_DT_F16 = 0, 1, 2
@@ -60,6 +69,7 @@ _i32, _i64, _f32, _p = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 SIGNATURES = {
     "rg_last_error": (C.c_char_p, []),
     "rg_version": (C.c_int, []),
+    "rg_operand_dtype": (C.c_int, []),
     "rg_launch_count": (C.c_int64, []),
     "rg_device_sm_count": (C.c_int, []),
     "rg_set_pdl": (C.c_int, [C.c_int]),
@@ -117,6 +127,9 @@ def load() -> C.CDLL:
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)        # AttributeError if the .so does not export a declared symbol
         fn.restype, fn.argtypes = res, args
+    want = RG_DT_F16 if OPERAND_DTYPE_NAME == "float16" else RG_DT_BF16
+    if lib.rg_operand_dtype() != want:
+        raise RestoragenError(f"{LIB_PATH} was built for another 16-bit operand type than {OPERAND_DTYPE_NAME}")
     _lib = lib
     return lib
 

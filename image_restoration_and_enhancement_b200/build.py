@@ -14,7 +14,9 @@ CSRC = HERE / "csrc"
 # RG_LIB_OUT=<path>: build an experimental variant (e.g. RG_NVCC_EXTRA=-DRG_GEMM_TUNING) next to the product library
 LIB = Path(os.environ["RG_LIB_OUT"]).resolve() if os.environ.get("RG_LIB_OUT") else HERE / "librestoragen.so"
 OBJDIR = HERE / ("build_alt" if os.environ.get("RG_LIB_OUT") else "build")
-STAMP = OBJDIR / "stamp.txt"
+# the fp16 parity build: the same sources with -DRG_OPERAND_F16 (see _lib.py / include/restoragen.h: rg_operand_dtype)
+LIB_F16 = HERE / "librestoragen_f16.so"
+OBJDIR_F16 = HERE / "build_f16"
 SOURCES = ["api.cu", "gemm.cu", "attention.cu", "norm.cu", "elementwise.cu", "metrics.cu", "lpips.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("RG_NVCC_EXTRA", "").split()
@@ -37,17 +39,25 @@ def _digest() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a and link librestoragen.so next to this file."""
-    digest = _digest()
+    """Compile every CUDA source for sm_100a and link librestoragen.so (bf16 operands, the product) and
+    librestoragen_f16.so (fp16 parity mode) next to this file.  Returns the product library."""
+    lib = _build_one(LIB, OBJDIR, [], force, verbose)
+    if not os.environ.get("RG_LIB_OUT"):
+        _build_one(LIB_F16, OBJDIR_F16, ["-DRG_OPERAND_F16"], force, verbose)
+    return lib
+
+
+def _build_one(LIB: Path, objdir: Path, extra: list, force: bool, verbose: bool) -> Path:
+    digest = _digest() + " " + " ".join(NVCC_FLAGS + extra)
+    STAMP = objdir / "stamp.txt"
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return LIB
     nvcc = _nvcc()
-    objdir = OBJDIR
     objdir.mkdir(exist_ok=True)
 
     def compile_one(src: str) -> Path:
         obj = objdir / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

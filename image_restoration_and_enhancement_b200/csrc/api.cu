@@ -1,6 +1,7 @@
 // Error reporting, launch accounting and the TMA tensor-map encoder for librestoragen.so.
 #include <atomic>
 #include <stdio.h>
+#include "common.cuh"
 #include "internal.h"
 
 namespace rg {
@@ -102,6 +103,7 @@ int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank
 
 extern "C" const char* rg_last_error(void) { return rg::g_err; }
 extern "C" int rg_version(void) { return 100; }
+extern "C" int rg_operand_dtype(void) { return rg::kOperandF16 ? RG_DT_F16 : RG_DT_BF16; }
 extern "C" int64_t rg_launch_count(void) { return rg::g_launches.load(); }
 extern "C" int rg_device_sm_count(void) { return rg::sm_count(); }
 extern "C" int rg_set_pdl(int mode) { return rg::g_pdl.exchange(mode & 3); }

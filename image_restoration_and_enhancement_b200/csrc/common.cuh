@@ -183,10 +183,15 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t saddr, uint
 }
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, dense, no negate.
 // b_mn_major = 1 when the B operand is MN-major in shared memory.
+#ifdef RG_OPERAND_F16
+#define RG_UMMA_AB_FMT 0u                  /* kind::f16 operand format 0 = fp16 */
+#else
+#define RG_UMMA_AB_FMT 1u                  /* 1 = bf16 */
+#endif
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4)                       // D format  = F32
-         | (1u << 7)                       // A format  = BF16
-         | (1u << 10)                      // B format  = BF16
+         | (RG_UMMA_AB_FMT << 7)           // A format  = the build's operand type (bf16; fp16 with -DRG_OPERAND_F16)
+         | (RG_UMMA_AB_FMT << 10)          // B format
          | ((uint32_t)a_mn_major << 15)
          | ((uint32_t)b_mn_major << 16)
          | ((uint32_t)(N >> 3) << 17)
@@ -313,18 +318,37 @@ __device__ __forceinline__ float gelu_fast_f(float x) {
     return x * (x >= 0.f ? 1.0f - h : h);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// ---- the 16-bit OPERAND type.  Product build: bf16 (fp32 range, the parity budget of DESIGN.md section 2).
+// -DRG_OPERAND_F16 (librestoragen_f16.so, "fp16 parity mode"): every 16-bit activation and weight in memory is IEEE fp16,
+// the dtype the reference runs on CUDA (src/inference.py:57, torch_dtype=float16), and the tensor cores multiply fp16
+// operands.  Pointers keep the __nv_bfloat16 element type (same size and alignment); ONLY these helpers and
+// umma_idesc_bf16 know which encoding the 16 bits hold, so no kernel has a second code path.
+#ifdef RG_OPERAND_F16
+constexpr bool kOperandF16 = true;
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) { return pack_f16x2(lo, hi); }
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+__device__ __forceinline__ __nv_bfloat16 f2op(float x) {
+    const __half h = __float2half_rn(x);
+    return *reinterpret_cast<const __nv_bfloat16*>(&h);
+}
+__device__ __forceinline__ float op2f(__nv_bfloat16 v) { return __half2float(*reinterpret_cast<const __half*>(&v)); }
+#else
+constexpr bool kOperandF16 = false;
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
     return __bfloat1622float2(v);
 }
+__device__ __forceinline__ __nv_bfloat16 f2op(float x) { return __float2bfloat16(x); }
+__device__ __forceinline__ float op2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+#endif
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

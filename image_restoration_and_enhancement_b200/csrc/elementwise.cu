@@ -54,7 +54,7 @@ __global__ void timestep_embedding_kernel(const float* t, int B, int dim, __nv_b
         const float freq = expf(-logf(10000.0f) * (float)f / (float)half);
         const float a = t[b] * freq;
         // flip_sin_to_cos: first half cos, second half sin
-        out[i] = __float2bfloat16(j < half ? cosf(a) : sinf(a));
+        out[i] = f2op(j < half ? cosf(a) : sinf(a));
     }
 }
 
@@ -78,10 +78,10 @@ __global__ void im2col_small_kernel(const void* x_, int N, int n_mod, int H, int
             if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
                 const long long idx = (((long long)n * H + ih) * W + iw) * Cin + c;
                 v = IN_F32 ? reinterpret_cast<const float*>(x_)[idx]
-                           : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x_)[idx]);
+                           : op2f(reinterpret_cast<const __nv_bfloat16*>(x_)[idx]);
             }
         }
-        out[i] = __float2bfloat16(v);
+        out[i] = f2op(v);
     }
 }
 
@@ -207,7 +207,7 @@ __global__ void scale_f32_kernel(const float* x, float a, long long n, float* y)
 __global__ void cast_f32_bf16_kernel(const float* x, long long n, __nv_bfloat16* y) {
     pdl_trigger();
     pdl_wait();
-    RG_GRID_STRIDE(i, n) y[i] = __float2bfloat16(x[i]);
+    RG_GRID_STRIDE(i, n) y[i] = f2op(x[i]);
 }
 
 }  // namespace rg
@@ -232,15 +232,16 @@ __global__ void embed_tokens_kernel(const int32_t* ids, const float4* tok, const
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* x, long long n, float* y) {
     pdl_trigger();
     pdl_wait();
-    RG_GRID_STRIDE(i, n) y[i] = __bfloat162float(x[i]);
+    RG_GRID_STRIDE(i, n) y[i] = op2f(x[i]);
 }
 // quick_gelu(x) = x * sigmoid(1.702 x), bf16 in place (CLIP MLP activation)
 __global__ void quick_gelu_bf16_kernel(__nv_bfloat162* x, long long n2) {
     pdl_trigger();
     pdl_wait();
     RG_GRID_STRIDE(i, n2) {
-        const float2 v = __bfloat1622float2(x[i]);
-        x[i] = __floats2bfloat162_rn(v.x / (1.f + __expf(-1.702f * v.x)), v.y / (1.f + __expf(-1.702f * v.y)));
+        const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(&x[i]));
+        const uint32_t o = pack_bf16x2(v.x / (1.f + __expf(-1.702f * v.x)), v.y / (1.f + __expf(-1.702f * v.y)));
+        x[i] = *reinterpret_cast<const __nv_bfloat162*>(&o);
     }
 }
 

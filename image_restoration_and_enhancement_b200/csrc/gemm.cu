@@ -814,11 +814,11 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
                                                 if (p.bias_n) y += __ldg(p.bias_n + (long long)g.n[i] * p.bias_n_ld + cidx);
                                                 if (p.res) {
                                                     y += p.res_f32 ? reinterpret_cast<const float*>(p.res)[g.off[i] + cidx]
-                                                                   : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[g.off[i] + cidx]);
+                                                                   : op2f(reinterpret_cast<const __nv_bfloat16*>(p.res)[g.off[i] + cidx]);
                                                 }
                                                 y = apply_act(y, p.act);
                                                 if (p.out_f32) p.out_f32[g.off[i] + cidx] = y;
-                                                if (p.out_bf16) { if (p.out_f16) reinterpret_cast<__half*>(p.out_bf16)[g.off[i] + cidx] = __float2half_rn(y); else p.out_bf16[g.off[i] + cidx] = __float2bfloat16(y); }
+                                                if (p.out_bf16) { if (p.out_f16) reinterpret_cast<__half*>(p.out_bf16)[g.off[i] + cidx] = __float2half_rn(y); else p.out_bf16[g.off[i] + cidx] = f2op(y); }
                                             }
                                         }
                                     }

@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__nv_bfloat16* x, int
     __nv_bfloat16* row = x + (long long)blockIdx.x * ld;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float m = -INFINITY;
-    for (int i = tid; i < cols; i += 256) m = fmaxf(m, __bfloat162float(row[i]));
+    for (int i = tid; i < cols; i += 256) m = fmaxf(m, op2f(row[i]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) red[warp] = m;
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__nv_bfloat16* x, int
     for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
     __syncthreads();
     float s = 0.f;
-    for (int i = tid; i < cols; i += 256) s += __expf(__bfloat162float(row[i]) - m);
+    for (int i = tid; i < cols; i += 256) s += __expf(op2f(row[i]) - m);
     s = warp_sum(s);
     if (lane == 0) red[warp] = s;
     __syncthreads();
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__nv_bfloat16* x, int
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += red[i];
     const float inv = 1.0f / s;
-    for (int i = tid; i < cols; i += 256) row[i] = __float2bfloat16(__expf(__bfloat162float(row[i]) - m) * inv);
+    for (int i = tid; i < cols; i += 256) row[i] = f2op(__expf(op2f(row[i]) - m) * inv);
 }
 
 }  // namespace rg

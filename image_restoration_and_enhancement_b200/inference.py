@@ -27,6 +27,7 @@ import numpy as np
 import torch
 from PIL import Image
 
+from ._lib import OPERAND_DTYPE_NAME as _OPERAND_DTYPE_NAME
 from .pipelines import StableDiffusionImg2ImgPipeline, StableDiffusionInpaintPipeline
 
 logger = logging.getLogger(__name__)
@@ -66,7 +67,7 @@ class RestorationPipeline:
     def __init__(self, device: str = "auto", config: dict | None = None, seed: int = 42, backend: str | None = None,
                  strict: bool = False):
         self.device = ("cuda" if torch.cuda.is_available() else "cpu") if device == "auto" else device
-        self.dtype = torch.bfloat16 if self.device == "cuda" else torch.float32
+        self.dtype = getattr(torch, _OPERAND_DTYPE_NAME) if self.device == "cuda" else torch.float32
         self.models: dict[str, object] = {}
         self._shared: dict[tuple, object] = {}
         self.seed = seed

@@ -30,7 +30,7 @@ from . import ops
 from ._lib import RG_ACT_RELU
 from .weights import pack_conv
 
-bf16, f32 = torch.bfloat16, torch.float32
+bf16, f32 = ops.OPERAND_DTYPE, torch.float32      # bf16 = the build's 16-bit operand dtype (ops.py)
 SHIFT = (-0.030, -0.088, -0.188)           # lpips.ScalingLayer
 SCALE = (0.458, 0.448, 0.450)
 CHANNELS = (64, 192, 384, 256, 256)

@@ -16,7 +16,10 @@ from . import _lib
 from ._lib import (RG_ACT_GEGLU, RG_ACT_NONE, RG_ACT_RELU, RG_ACT_SILU, RG_DT_BF16, RG_DT_F16, RG_DT_F32, RgAct, RgAttn, RgConv, RgGn,
                    RgSched, check)
 
-bf16, f32, f16 = torch.bfloat16, torch.float32, torch.float16
+# `bf16` is the build's 16-bit OPERAND dtype: torch.bfloat16 with librestoragen.so, torch.float16 in the fp16 parity mode
+# (RESTORAGEN_OPERAND_DTYPE=fp16 -> librestoragen_f16.so, see _lib.py); the C ABI calls it RG_DT_BF16 either way
+bf16, f32, f16 = getattr(torch, _lib.OPERAND_DTYPE_NAME), torch.float32, torch.float16
+OPERAND_DTYPE = bf16
 GN_MAX_IMAGES = 1024      # RG_GN_MAX_IMAGES: fixed-size counter area in front of the GroupNorm workspace
 GN_MAX_BLOCKS = 256       # RG_GN_MAX_BLOCKS in include/restoragen.h
 
@@ -176,7 +179,7 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, *, kh: int = 1, kw: int = 1, stride
     if out_bf16 is not None:
         assert out_bf16.dtype in (bf16, f16)
         p.out_bf16 = out_bf16.data_ptr()
-        p.out16_dtype = RG_DT_F16 if out_bf16.dtype == f16 else RG_DT_BF16
+        p.out16_dtype = RG_DT_F16 if (out_bf16.dtype == f16 and bf16 is not f16) else RG_DT_BF16
     if out_f32 is not None:
         assert out_f32.dtype == f32
         p.out_f32 = out_f32.data_ptr()
@@ -224,7 +227,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, o
     p.v_stride_b, p.v_stride_t, p.v_stride_h = v.stride(0), v.stride(1), v.stride(2)
     p.o_stride_b, p.o_stride_t, p.o_stride_h = out.stride(0), out.stride(1), out.stride(2)
     p.scale = scale
-    p.dtype = RG_DT_F16 if q.dtype == f16 else RG_DT_BF16
+    # fp16 kernels (ones-column row sums) exist for the UNet's head dims; everything else takes the operand-dtype path
+    p.dtype = RG_DT_F16 if (q.dtype == f16 and (bf16 is not f16 or (not causal and d in (40, 80, 160)))) else RG_DT_BF16
     p.causal = 1 if causal else 0
     e0 = _prof_begin()
     check(lib.rg_attention(C.byref(p), _stream()), "rg_attention")

@@ -18,7 +18,7 @@ import torch
 
 from . import ops
 
-bf16, f32 = torch.bfloat16, torch.float32
+bf16, f32 = ops.OPERAND_DTYPE, torch.float32      # bf16 = the build's 16-bit operand dtype (ops.py)
 
 
 class CLIPTextB200:

@@ -22,7 +22,7 @@ from . import ops
 from ._lib import RG_ACT_GEGLU, RG_ACT_SILU
 from .weights import interleave_geglu, pack_conv, unet_param_shapes, upsample_parity_weights
 
-bf16, f32, f16 = torch.bfloat16, torch.float32, torch.float16
+bf16, f32, f16 = ops.OPERAND_DTYPE, torch.float32, torch.float16      # bf16 = the build's 16-bit operand dtype (ops.py)
 
 
 class _Resnet:

@@ -17,7 +17,7 @@ import torch
 from . import ops
 from .weights import pack_conv, upsample_parity_weights, vae_param_shapes
 
-bf16, f32 = torch.bfloat16, torch.float32
+bf16, f32 = ops.OPERAND_DTYPE, torch.float32      # bf16 = the build's 16-bit operand dtype (ops.py)
 
 
 class _VResnet:

@@ -49,6 +49,11 @@ typedef void* rg_stream_t; /* cudaStream_t */
 
 const char* rg_last_error(void);
 int rg_version(void);
+/* Encoding of every 16-bit activation / weight this build reads and writes (the buffers the structs below call "bf16"):
+   RG_DT_BF16 for librestoragen.so (the product), RG_DT_F16 for librestoragen_f16.so -- the same sources compiled with
+   -DRG_OPERAND_F16, the "fp16 parity mode": fp16 storage and fp16 tensor-core operands end to end, the dtype the
+   reference runs on CUDA (src/inference.py:57 and :162-166, torch_dtype=torch.float16).  A process uses one of the two. */
+int rg_operand_dtype(void);
 /* number of kernel launches issued by this library in the calling process (all threads) */
 int64_t rg_launch_count(void);
 int rg_device_sm_count(void);

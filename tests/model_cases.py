@@ -137,9 +137,12 @@ def case_vae_decode(B=1, h=64, w=64, seed=1):
 
 # ------------------------------------------------------------------------------------------------ whole pipeline
 @torch.no_grad()
-def case_pipeline(task="denoise", H=512, W=512, B=1, seed=0, graph=True):
+def case_pipeline(task="denoise", H=512, W=512, B=1, seed=0, graph=True, steps=None, oracle_images=None, step_stride=1):
     """Full sampling run vs the oracle pipeline: per-step guided-eps rel-L2 (each step fed the CUDA path's own
-    UNet input, so the figure isolates one UNet evaluation) and PSNR of the final uint8 image."""
+    UNet input, so the figure isolates one UNet evaluation) and PSNR of the final uint8 image.
+    ``steps`` overrides num_inference_steps (BASELINE config 4 runs 50); ``oracle_images`` = indices of the batch the
+    oracle re-runs and the image / latent comparisons cover (default: all); ``step_stride``: every n-th UNet step is
+    replayed through the oracle UNet (default: every step)."""
     _setup()
     from oracle.pipelines import OraclePipeline, Trace
     params = {"denoise": dict(steps=20, strength=0.5, g=5.0, kind="pndm", cin=4),
@@ -147,6 +150,9 @@ def case_pipeline(task="denoise", H=512, W=512, B=1, seed=0, graph=True):
               "sr": dict(steps=20, strength=0.8, g=0.0, kind="pndm", cin=4),
               "inpaint": dict(steps=30, strength=0.6, g=5.0, kind="ddim", cin=9)}[task]
     cin = params["cin"]
+    if steps is not None:
+        params["steps"] = steps
+    idx = list(range(B)) if oracle_images is None else list(oracle_images)
     ou, usd = oracle_unet(cin, seed)
     ov, vsd = oracle_vae(seed + 1)
     cls = StableDiffusionInpaintPipeline if cin == 9 else StableDiffusionImg2ImgPipeline
@@ -181,27 +187,29 @@ def case_pipeline(task="denoise", H=512, W=512, B=1, seed=0, graph=True):
     x = (torch.from_numpy(img).to(DEV).float() / 255.0).permute(0, 3, 1, 2) * 2.0 - 1.0
     otrace = Trace()
     refs = []
-    for i in range(B):
+    for i in idx:
         gi = torch.Generator(device=DEV).manual_seed(42)
         if cin == 9:
             m = (torch.from_numpy(mask[i:i + 1]).to(DEV).float() / 255.0 >= 0.5).float()[:, None]
             refs.append(op.inpaint(x[i:i + 1], m, pe, ne, strength=params["strength"],
                                    num_inference_steps=params["steps"], guidance_scale=params["g"], generator=gi,
-                                   trace=otrace if i == 0 else None))
+                                   trace=otrace if i == idx[0] else None))
         else:
             refs.append(op.img2img(x[i:i + 1], pe, ne, strength=params["strength"],
                                    num_inference_steps=params["steps"], guidance_scale=params["g"], generator=gi,
-                                   trace=otrace if i == 0 else None))
+                                   trace=otrace if i == idx[0] else None))
     ref = np.concatenate(refs)
-    res = {"psnr": psnr_u8(out, ref), "steps": len(trace["timesteps"]), "timesteps_match": trace["timesteps"] == otrace.timesteps}
-    res["init_latents_rel"] = rel_l2(ops.nhwc_to_nchw(trace["init_latents"])[0:1], otrace.init_latents)
-    res["final_latents_rel"] = rel_l2(ops.nhwc_to_nchw(trace["final_latents"])[0:1], otrace.final_latents)
+    i0 = idx[0]                                          # the image whose latent trajectory the oracle traced
+    res = {"psnr": min(psnr_u8(out[i:i + 1], ref[k:k + 1]) for k, i in enumerate(idx)), "steps": len(trace["timesteps"]),
+           "timesteps_match": trace["timesteps"] == otrace.timesteps}
+    res["init_latents_rel"] = rel_l2(ops.nhwc_to_nchw(trace["init_latents"])[i0:i0 + 1], otrace.init_latents)
+    res["final_latents_rel"] = rel_l2(ops.nhwc_to_nchw(trace["final_latents"])[i0:i0 + 1], otrace.final_latents)
     # per-step UNet error with the CUDA path's own inputs replayed through the oracle UNet
     do_cfg = params["g"] > 1.0
     Bu = 2 * B if do_cfg else B
     embeds = torch.cat([ne.repeat(B, 1, 1), pe.repeat(B, 1, 1)]) if do_cfg else pe.repeat(B, 1, 1)
     step_err = []
-    for i in range(len(trace["timesteps"])):            # EVERY step of the run
+    for i in range(0, len(trace["timesteps"]), step_stride):      # EVERY step of the run unless a stride is given
         xin = ops.nhwc_to_nchw(trace["unet_in"][i].contiguous())
         xin = torch.cat([xin] * 2) if do_cfg else xin
         ref_eps = ou(xin, torch.tensor(float(trace["timesteps"][i]), device=DEV), embeds)
@@ -209,7 +217,7 @@ def case_pipeline(task="denoise", H=512, W=512, B=1, seed=0, graph=True):
         step_err.append(rel_l2(got, ref_eps))
     res["unet_step_rel"] = step_err
     # scheduler-state parity along the whole trajectory: the CUDA path's latents after every step against the oracle's
-    res["latents_rel_per_step"] = [rel_l2(ops.nhwc_to_nchw(a.contiguous())[0:1], b)
+    res["latents_rel_per_step"] = [rel_l2(ops.nhwc_to_nchw(a.contiguous())[i0:i0 + 1], b)
                                    for a, b in zip(trace["latents"], otrace.latents)]
     return res
 

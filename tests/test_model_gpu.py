@@ -59,6 +59,41 @@ def test_pipeline_vs_oracle(task):
     assert max(r["latents_rel_per_step"]) <= mc.LATENT_TOL, r
 
 
+@pytest.mark.parametrize("task,B,steps,expect_steps", [("colorize", 8, None, 23), ("inpaint", 8, None, 18), ("sr", 4, 50, 41)])
+def test_pipeline_vs_oracle_at_baseline_batch(task, B, steps, expect_steps):
+    """BASELINE.json configs 2-4 at their own batch sizes and step counts (colorize / inpaint batch 8, sr batch 4 x 50
+    steps): the first and the last image of the batch against per-image oracle runs (the reference's own loop is per
+    image), every 4th UNet step of the whole batch replayed through the oracle UNet."""
+    r = mc.case_pipeline(task, B=B, steps=steps, oracle_images=(B - 1, 0), step_stride=4)
+    print(f"{task} B={B}: psnr {r['psnr']:.2f} max-step {max(r['unet_step_rel']):.3e} final {r['final_latents_rel']:.3e}")
+    assert r["timesteps_match"] and r["steps"] == expect_steps
+    assert max(r["unet_step_rel"]) <= mc.UNET_TOL, r
+    assert r["psnr"] >= mc.PSNR_MIN, r
+    assert r["init_latents_rel"] <= mc.LATENT_TOL and r["final_latents_rel"] <= mc.LATENT_TOL, r
+    assert max(r["latents_rel_per_step"]) <= mc.LATENT_TOL, r
+
+
+def test_fp16_parity_mode():
+    """SURVEY 8f "f4": the fp16 parity mode -- RESTORAGEN_OPERAND_DTYPE=fp16 loads librestoragen_f16.so (same sources,
+    -DRG_OPERAND_F16): every 16-bit activation / weight is fp16 and the tensor cores multiply fp16 operands, the dtype the
+    reference runs on CUDA (src/inference.py:57, :162-166).  Own process (the dtype is chosen at import); same gates as the
+    bf16 product against the fp32 oracle."""
+    import json, os, subprocess, sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    env = dict(os.environ, RESTORAGEN_OPERAND_DTYPE="fp16")
+    r = subprocess.run([sys.executable, str(root / "tools" / "gpu_fp16_mode_check.py")], capture_output=True, text=True,
+                       env=env, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    print(d)
+    assert d["library"] == "librestoragen_f16.so" and d["operand_dtype"] == "torch.float16" and d["rg_operand_dtype"] == 2
+    assert d["unet_rel_l2"] <= mc.UNET_TOL and d["unet9_rel_l2"] <= mc.UNET_TOL, d
+    assert d["vae_encode_rel_l2"] <= 1e-2 and d["vae_decode_rel_l2"] <= 1e-2 and d["vae_decode_psnr"] >= mc.PSNR_MIN, d
+    dn = d["denoise"]
+    assert dn["timesteps_match"] and dn["steps"] == 11 and dn["max_unet_step_rel"] <= mc.UNET_TOL and dn["psnr"] >= mc.PSNR_MIN, d
+
+
 def test_batched_call_equals_separate_calls():
     """B images with per-image generators (same seed) == B separate reference-style calls."""
     from image_restoration_and_enhancement_b200.pipelines import StableDiffusionImg2ImgPipeline

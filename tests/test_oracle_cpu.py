@@ -258,6 +258,12 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert _lib.load().rg_version() >= 100
+    # the two builds of the same sources: bf16 operands (the product) and the fp16 parity mode
+    assert _lib.load().rg_operand_dtype() == _lib.RG_DT_BF16
+    lib16 = ctypes.CDLL(str(build.LIB_F16))
+    for name in declared:
+        assert hasattr(lib16, name), name
+    assert lib16.rg_operand_dtype() == _lib.RG_DT_F16
     sizes = {"rg_conv_t": ctypes.sizeof(_lib.RgConv), "rg_attn_t": ctypes.sizeof(_lib.RgAttn)}
     assert sizes["rg_conv_t"] % 8 == 0 and sizes["rg_attn_t"] % 8 == 0
 
