@@ -283,11 +283,17 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc,
 }
 // Arrives (once) on the mbarrier at the same shared-memory offset in both CTAs of the pair when every previously
 // issued tcgen05.mma of this thread has completed.
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+// `cta_mask`: the two CTAs of the pair inside the cluster (3 for a cluster that IS the pair, 3 << 2k for pair k of a larger one).
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask = 3) {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+        ::"r"(smem_u32(bar)), "h"(cta_mask)
         : "memory");
+}
+// 16-byte store into the shared memory of another CTA of the cluster (address from mapa_shared)
+__device__ __forceinline__ void st_cluster_f4(uint32_t cluster_addr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
 }
 
 // ------------------------------------------------------------------------------------ math

@@ -515,8 +515,147 @@ __device__ __noinline__ void epilogue_splitk(const GemmParams& p, uint8_t* stagi
     __syncwarp();
 }
 
-template <int BNC, int NC, int EW>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((EW + 2) * 32, 1)
+// ---------------------------------------------------------------------------------------------------------------
+// In-cluster split-K (CKS = 2 or 4 K slices; NC = 1, EW = 16): the few-tile, long-K layers of the small UNet batches.
+// A cluster of CKS CTA pairs computes ONE output tile, pair s the K slice s, and the partial tiles meet in shared
+// memory instead of in an L2 workspace:
+//   send   after a cluster barrier (every pair's MMAs have retired, so the operand rings are free), every epilogue warp
+//          reads its accumulator units from TMEM and stores them into the ring of the CTA that OWNS its 32-row quarter
+//          (quarter q belongs to pair q % CKS, same rank) -- st.shared::cluster, lane-interleaved float4s;
+//   final  after a second cluster barrier, every CTA holds the CKS partials of the row quarters it owns: its 16 warps take
+//          one 16-column unit each, add the partials in slice order 0..CKS-1 (fixed: bitwise reproducible), apply scale /
+//          bias / per-image bias / residual / activation and hand the box to a TMA store.
+// Against the workspace version (epilogue_splitk) this removes the dump to L2, two gpu-scope fences, the arrival atomics
+// and the serial chain of L2 round trips in the last-arriving warp: the fix-up costs two cluster barriers and one unit
+// per warp.  One tile per cluster and no persistence (grid = tiles x 2 CKS CTAs), so both barriers are executed exactly
+// once by every thread of the cluster.
+template <int BNC, int EW, int CKS>
+__device__ __forceinline__ void cluster_splitk_send(uint8_t* ring, uint32_t tmem_base, uint32_t rank, uint32_t pair, int warp, int lane) {
+    constexpr int UPC = BNC / 16, PARTS = EW / 4, QPP = 4 / CKS;      // units per tile, warps per quarter, quarters per pair
+    const int ew = warp - 2, q = warp & 3, part = ew >> 2;
+    const uint32_t owner = (uint32_t)(q % CKS), q_local = (uint32_t)(q / CKS);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t dst0 = mapa_shared(smem_u32(ring), owner * 2 + rank) + ((pair * QPP + q_local) * UPC) * 2048u + lane * 16u;
+#pragma unroll 1
+    for (int u = part; u < UPC; u += PARTS) {
+        uint32_t va[16];
+        tmem_ld16(taddr + u * 16, va);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            st_cluster_f4(dst0 + u * 2048u + j * 512u, make_float4(__uint_as_float(va[4 * j]), __uint_as_float(va[4 * j + 1]),
+                                                                   __uint_as_float(va[4 * j + 2]), __uint_as_float(va[4 * j + 3])));
+    }
+}
+
+template <int BNC, int EW, int CKS>
+__device__ __noinline__ void cluster_splitk_final(const GemmParams& p, const uint8_t* ring, uint8_t* staging, uint32_t rank,
+                                                  uint32_t pair, int t2, int warp, int lane) {
+    using Cfg = GemmCfg<BNC, 1, EW>;
+    constexpr int UPC = BNC / 16, QPP = 4 / CKS, HBUF = Cfg::HBUF;
+    const int ew = warp - 2;
+    uint8_t* const pbuf0 = staging + ew * Cfg::WARP_STAGING;
+    uint8_t* const hbuf0 = pbuf0 + Cfg::NBUF * 2048;
+    const int TW = 1 << p.lw, TH = 1 << p.lh, lwh = p.lw + p.lh, TN = 128 >> lwh;
+    const int sw = (lane >> 1) & 3, fo = lane * 64, ho = lane * 32, hsw = (lane >> 2) & 1;
+    const bool prim_f32 = p.prim_f32 != 0, prim_store = p.prim_store != 0, sec_store = p.sec_store != 0;
+    const bool silu = p.act == 1, relu = p.act == 3, out_f16 = p.out_f16 != 0, res_f32 = p.res_f32 != 0;
+    const float scale = p.scale;
+    const int n_tiles_n = p.n_tiles_n, tiles_w = p.tiles_w, tiles_h = p.tiles_h, lw = p.lw;
+    const int pOW = p.OW, pOH = p.OH, pN = p.N;
+    const long long osn = p.osn, osh = p.osh, osw = p.osw, bias_n_ld = p.bias_n_ld;
+    const float* const bias = p.bias;
+    const float* const bias_n = p.bias_n;
+    const void* const res = p.res;
+    const CUtensorMap* const pmap = &p.pmap;
+    const CUtensorMap* const hmap = &p.hmap;
+    auto pack16 = [&](float lo, float hi) { return out_f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); };
+    const int mp = t2 / n_tiles_n, n_tile = t2 - mp * n_tiles_n;
+    const int m_tile = 2 * mp + (int)rank;
+    const int twi = m_tile % tiles_w;
+    const int rest = m_tile / tiles_w;
+    const int thi = rest % tiles_h, tni = rest / tiles_h;
+    pdl_wait();                                           // parameters are in registers; global memory from here on
+    uint32_t A = 0;
+#pragma unroll 1
+    for (int item = ew; item < QPP * UPC; item += EW) {
+        const int q_local = item / UPC, u = item - q_local * UPC;
+        const int q = q_local * CKS + (int)pair;          // the row quarter (TMEM lane quarter of the senders) this CTA owns
+        const int row0 = q * 32, row = row0 + lane;
+        const int cw = twi * TW + (row0 & (TW - 1)), ch = thi * TH + ((row0 >> lw) & (TH - 1)), cn = tni * TN + (row0 >> lwh);
+        const int ow = twi * TW + (row & (TW - 1)), oh = thi * TH + ((row >> lw) & (TH - 1)), n = tni * TN + (row >> lwh);
+        const bool valid = ow < pOW && oh < pOH && n < pN;
+        if (!__any_sync(0xffffffffu, valid)) continue;    // all-padding quarter (odd last tile, M < 256)
+        const long long off = valid ? (long long)n * osn + (long long)oh * osh + (long long)ow * osw : 0;
+        const float* const bn_row = bias_n ? bias_n + (long long)(n < pN ? n : pN - 1) * bias_n_ld : nullptr;
+        const int gcol = n_tile * BNC + u * 16;
+        uint8_t* const pb = pbuf0 + (A % 2) * 2048;
+        uint8_t* const hb = hbuf0 + (A % HBUF) * 1024;
+        if (lane == 0) {                                   // the store that last used these buffers has drained them
+            if (HBUF >= 2 || !sec_store) bulk_wait_read<1>(); else bulk_wait_read<0>();
+        }
+        __syncwarp();
+        // partials of slices 0..CKS-1, added in slice order
+        float4 sum[4];
+        const float4* const src = reinterpret_cast<const float4*>(ring + (size_t)(q_local * UPC + u) * 2048) + lane;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sum[j] = src[j * 32];
+#pragma unroll
+        for (int s = 1; s < CKS; ++s) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 v = src[(size_t)s * QPP * UPC * 128 + j * 32];
+                sum[j].x += v.x; sum[j].y += v.y; sum[j].z += v.z; sum[j].w += v.w;
+            }
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 a = sum[j];
+            float y0 = a.x * scale, y1 = a.y * scale, y2 = a.z * scale, y3 = a.w * scale;
+            if (bias) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + gcol + 4 * j));
+                y0 += bv.x; y1 += bv.y; y2 += bv.z; y3 += bv.w;
+            }
+            if (bn_row) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(bn_row + gcol + 4 * j));
+                y0 += bv.x; y1 += bv.y; y2 += bv.z; y3 += bv.w;
+            }
+            if (res && valid) {
+                if (res_f32) {
+                    const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(res) + off + gcol + 4 * j);
+                    y0 += r.x; y1 += r.y; y2 += r.z; y3 += r.w;
+                } else {
+                    const uint2 r2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(res) + off + gcol + 4 * j);
+                    const float2 f0 = unpack_bf16x2(r2.x), f1 = unpack_bf16x2(r2.y);
+                    y0 += f0.x; y1 += f0.y; y2 += f1.x; y3 += f1.y;
+                }
+            }
+            if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+            if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
+            if (prim_f32 && prim_store) *reinterpret_cast<float4*>(pb + fo + ((j ^ sw) << 4)) = make_float4(y0, y1, y2, y3);
+            pk[2 * j] = pack16(y0, y1); pk[2 * j + 1] = pack16(y2, y3);
+        }
+        if (!prim_f32 || sec_store) {
+            uint8_t* const bb = prim_f32 ? hb : pb;
+            *reinterpret_cast<uint4*>(bb + ho + (hsw << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(bb + ho + ((hsw ^ 1) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            if (prim_store) tma_store_4d(pmap, pb, gcol, cw, ch, cn);
+            if (sec_store) tma_store_4d(hmap, hb, gcol, cw, ch, cn);
+            bulk_commit();
+        }
+        ++A;
+    }
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+}
+
+template <int BNC, int NC, int EW, int CKS = 0>
+__global__ void __cluster_dims__(CKS > 0 ? 2 * CKS : 2, 1, 1) __launch_bounds__((EW + 2) * 32, 1)
 conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BNC, NC, EW>;
     extern __shared__ uint8_t smem_raw[];
@@ -532,8 +671,13 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    // the cluster is one CTA pair, or (CKS > 0, in-cluster split-K) CKS pairs: pair k = cluster ranks 2k, 2k + 1
+    static_assert(CKS == 0 || ((CKS == 2 || CKS == 4) && NC == 1 && EW == 16), "in-cluster split-K: 2 or 4 slices of the 1 x BNC tile");
+    constexpr int CSZ = CKS > 0 ? 2 * CKS : 2;
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t rank = crank & 1, pair = crank >> 1, leader = crank & ~1u;
+    const uint16_t pair_mask = (uint16_t)(3u << leader);
+    const int cluster_id = blockIdx.x / CSZ, n_clusters = gridDim.x / CSZ;
 
     pdl_trigger();                      // the next kernel may be scheduled now (it waits for this one before touching memory)
     if (warp == 0 && lane == 0) {
@@ -559,13 +703,16 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     // work items: (pair of 128-pixel tiles, column tile, K split); the K split is the fastest index
     const int total_tiles = p.n_pairs_m * p.n_tiles_n * p.ksplit;
     const int TW = 1 << p.lw, TH = 1 << p.lh;
+    // in-cluster split-K: exactly one work item per pair -- output tile = cluster, K slice = pair (p.ksplit == CKS)
+    const int tile_first = CKS > 0 ? cluster_id * CKS + (int)pair : cluster_id;
+    const int tile_step = CKS > 0 ? total_tiles : n_clusters;
 
     if (warp == 0) {
         // ===================================================================== TMA producer (both CTAs)
         if (lane == 0) {
             pdl_wait();
             int stage = 0; uint32_t phase = 0;
-            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+            for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
                 const int ks = tile % p.ksplit, t2 = tile / p.ksplit;
                 const int mp = t2 / p.n_tiles_n, n_tile = t2 - mp * p.n_tiles_n;
                 const int m_tile = 2 * mp + (int)rank;
@@ -582,7 +729,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
                     for (int cb = kblk < kb0 ? kb0 - kblk : 0; cb < item.nblk && kblk + cb < kb1; ++cb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                        const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                        const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), leader);
                         if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
                         tma_load_4d_pair(sa, &p.amap[item.map], fb, cb * 64, w0 + item.dw, h0 + item.dh, n0);
 #pragma unroll
@@ -602,7 +749,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
             constexpr uint32_t idesc = umma_idesc_bf16(256, BNC, 0, 0);
             int stage = 0; uint32_t phase = 0;
             uint32_t cc = 0;                                   // accumulator chunks started so far (ring position)
-            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, cc += NC) {
+            for (int tile = tile_first; tile < total_tiles; tile += tile_step, cc += NC) {
                 uint32_t d_tmem[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
@@ -627,16 +774,19 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
                             umma_bf16_pair(d_tmem[c], adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
                     }
-                    umma_commit_pair(&empty_bar[stage]);        // frees the stage in both CTAs when these MMAs retire
+                    umma_commit_pair(&empty_bar[stage], pair_mask);   // frees the stage in both CTAs when these MMAs retire
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
 #pragma unroll
-                for (int c = 0; c < NC; ++c) umma_commit_pair(&acc_full[(cc + c) % Cfg::SLOTS]);
+                for (int c = 0; c < NC; ++c) umma_commit_pair(&acc_full[(cc + c) % Cfg::SLOTS], pair_mask);
             }
         }
     } else {
         // ===================================================================== epilogue (both CTAs, own 128 rows)
-        if (p.ksplit > 1) {
+        if constexpr (CKS > 0) {
+            mbar_wait(&acc_full[0], 0);                 // this pair's K slice is accumulated (send / final follow below)
+            tc_fence_after();
+        } else if (p.ksplit > 1) {
             if constexpr (NC == 1)
                 epilogue_splitk<BNC, EW>(p, staging, acc_full, acc_empty, tmem_base, rank, cluster_id, n_clusters, warp, lane);
         } else if (p.epi_tma) {
@@ -835,6 +985,13 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         }
     }
 
+    if constexpr (CKS > 0) {
+        __syncwarp();
+        cluster_sync_all();             // every pair's MMAs have retired: all operand rings of the cluster are free
+        if (warp >= 2) cluster_splitk_send<BNC, EW, CKS>(smem, tmem_base, rank, pair, warp, lane);
+        cluster_sync_all();             // the partials have landed in their owners' rings
+        if (warp >= 2) cluster_splitk_final<BNC, EW, CKS>(p, smem, staging, rank, pair, cluster_id, warp, lane);
+    }
     tc_fence_before();
     cluster_sync_all();                 // the peer may still be reading this CTA's shared memory / signalling its barriers
     if (warp == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
@@ -853,11 +1010,12 @@ static int encode_act_map(CUtensorMap* m, const void* base, int C, long long W, 
                              CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BNC, int NC, int EW = 8>
+template <int BNC, int NC, int EW = 8, int CKS = 0>
 static int launch_gemm(GemmParams& gp, const void* w, long long ktot, long long w_ld, cudaStream_t stream) {
     using Cfg = GemmCfg<BNC, NC, EW>;
+    static_assert(CKS == 0 || 4 * (BNC / 16) * 2048 <= Cfg::STAGES * Cfg::STAGE_BYTES, "CKS partials of the owned row quarters must fit in the operand ring");
     static std::atomic<bool> attr_done[kMaxDevices];
-    if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&conv_gemm_kernel<BNC, NC, EW>), Cfg::SMEM_BYTES, attr_done,
+    if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&conv_gemm_kernel<BNC, NC, EW, CKS>), Cfg::SMEM_BYTES, attr_done,
                                   "cudaFuncSetAttribute(conv_gemm_kernel)")) return rc;
     {
         cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)gp.Cout};
@@ -873,14 +1031,49 @@ static int launch_gemm(GemmParams& gp, const void* w, long long ktot, long long 
     const int total = gp.n_pairs_m * gp.n_tiles_n * gp.ksplit;
     const int max_clusters = sm_count() / 2;
     const int clusters = total < max_clusters ? total : max_clusters;
-    launch_kernel(conv_gemm_kernel<BNC, NC, EW>, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, gp);
+    // in-cluster split-K: one cluster of CKS pairs per output tile, not persistent (the hardware queues clusters that do
+    // not fit at once; they are independent)
+    const int ctas = CKS > 0 ? 2 * total : 2 * clusters;
+    launch_kernel(conv_gemm_kernel<BNC, NC, EW, CKS>, dim3(ctas), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, gp);
     count_launch();
     return check_launch("conv_gemm_kernel");
+}
+
+// How many clusters of CKS pairs the device can hold at once (one CTA per SM at this shared-memory footprint; a cluster
+// needs CKS whole TPCs inside one GPC).  The in-cluster split-K is only chosen when every output tile's cluster is
+// resident in the first wave.
+template <int CKS>
+static int max_active_clusters() {
+    using Cfg = GemmCfg<160, 1, 16>;
+    static std::atomic<int> cache[kMaxDevices];
+    const int dev = current_device();
+    int n = cache[dev].load();
+    if (n > 0) return n;
+    static std::atomic<bool> attr_done[kMaxDevices];
+    if (ensure_smem_attr(reinterpret_cast<const void*>(&conv_gemm_kernel<160, 1, 16, CKS>), Cfg::SMEM_BYTES, attr_done,
+                         "cudaFuncSetAttribute(conv_gemm_kernel)")) return 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * CKS * 64); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2 * CKS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<160, 1, 16, CKS>, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = CKS == 4 ? 14 : 30;          // conservative: B200 has 74 TPCs in 8 GPCs
+    }
+    cache[dev].store(n);
+    return n;
 }
 
 }  // namespace rg
 
 using namespace rg;
+
+// Debug hook (not part of the public header): clusters of `cks` CTA pairs the current device holds at once.
+extern "C" int rg_debug_max_active_clusters(int cks) { return cks == 4 ? max_active_clusters<4>() : max_active_clusters<2>(); }
 
 extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -1056,6 +1249,28 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
         if (gp.total_kblk >= 48 && tiles160 * 2 <= clusters) {
             ks = 8;
             while (ks > 1 && (ks * tiles160 > clusters || ks > gp.total_kblk / 12)) ks >>= 1;
+        }
+        // ---- first choice: the K slices of a tile inside ONE cluster (4 or 2 CTA pairs), partials exchanged through
+        // shared memory (cluster_splitk_send / _final) -- when every tile's cluster fits on the device at once
+        if (ks > 1) {
+            // Measured (profiles/r02_cluster_splitk.txt): the main loop of these layers runs at ~0.29 us per k-block whichever
+            // way the K slices meet (operand fetch, not MMA), the in-cluster fix-up saves 3.5-8 us per launch, and a launch
+            // that engages half as many pairs loses that again after ~45 k-blocks.  So: in-cluster when it engages as many
+            // pairs as the workspace version would, or when its slices are short anyway.
+            int cks = 0;
+            if (tiles160 * 4 <= clusters && tiles160 <= max_active_clusters<4>()) cks = 4;
+            else if (tiles160 <= max_active_clusters<2>()) cks = 2;
+            if (cks && cks < ks && (gp.total_kblk + cks - 1) / cks > 48) cks = 0;
+#ifdef RG_GEMM_TUNING
+            { const char* e = getenv("RG_GEMM_CLUSTER"); if (e) { const int v = atoi(e); if (v == 0) cks = 0; else if (v == 2 && cks == 4) cks = 2; } }
+#endif
+            const int kper = cks ? (gp.total_kblk + cks - 1) / cks : 0;
+            if (cks && (long long)kper * (cks - 1) < gp.total_kblk) {
+                gp.ksplit = cks;
+                gp.kper = kper;
+                return cks == 4 ? launch_gemm<160, 1, 16, 4>(gp, c->w, ktot, w_ld, stream)
+                                : launch_gemm<160, 1, 16, 2>(gp, c->w, ktot, w_ld, stream);
+            }
         }
         if (ks > 1) {
             // 16 epilogue warps: 2-3 units per warp instead of 5 -- the fix-up of a tile is a serial chain of units in the
