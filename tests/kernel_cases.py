@@ -314,11 +314,10 @@ def case_groupnorm(N=2, H=16, W=16, C1=320, C2=0, in_f32=True, silu=True, eps=1e
     return err, TOL_BF16
 
 
-def case_groupnorm_shapes_agree(seed=34):
+def case_groupnorm_shapes_agree(seed=34, N=16, H=16, W=16, C1=640, C2=320):
     """GroupNorm is batch-invariant BITWISE: a batch of 16 against each image normalised on its own (fp32 two-source
     input with raw copy)."""
     _setup()
-    N, H, W, C1, C2 = 16, 16, 16, 640, 320
     x1 = _rand((N, H, W, C1), seed, 1.5, torch.float32) + 0.3
     x2 = _rand((N, H, W, C2), seed + 1, 0.7, torch.float32) - 0.2
     gamma = _rand((C1 + C2,), seed + 2, 0.2, torch.float32) + 1.0
@@ -327,7 +326,7 @@ def case_groupnorm_shapes_agree(seed=34):
     ref = F.silu(F.group_norm(torch.cat([x1, x2], dim=3).permute(0, 3, 1, 2), 32, gamma, beta, 1e-5))
     err = rel_l2(y.float().permute(0, 3, 1, 2), ref)
     bad = 0
-    for n in (0, 7, 15):
+    for n in (0, N // 2, N - 1):
         y1, r1 = ops.groupnorm(x1[n:n + 1].contiguous(), gamma, beta, silu=True, x2=x2[n:n + 1].contiguous(), want_raw=True)
         torch.cuda.synchronize()
         bad += int((y1 != y[n:n + 1]).sum()) + int((r1 != r[n:n + 1]).sum())
@@ -587,6 +586,12 @@ CASES = {
     "gn_64x64_c320_f32_n2": lambda: case_groupnorm(N=2, H=64, W=64, C1=320, seed=38),
     "gn_64x64_concat640_bf16_n3": lambda: case_groupnorm(N=3, H=64, W=64, C1=320, C2=320, in_f32=False, raw=True, seed=39),
     "gn_32x32_concat1280_f32_n2": lambda: case_groupnorm(N=2, H=32, W=32, C1=640, C2=640, raw=True, seed=40),
+    # --- one-pass cluster kernel (64x64 level: 8 blocks per (image, 80-channel block), partials through DSMEM)
+    "gn_cluster_concat640_f32_raw": lambda: case_groupnorm(N=2, H=64, W=64, C1=320, C2=320, raw=True, seed=141),
+    "gn_cluster_ragged_62x41": lambda: case_groupnorm(N=3, H=62, W=41, C1=320, silu=False, seed=142),
+    "gn_cluster_c320_bf16_n16": lambda: case_groupnorm(N=16, H=64, W=64, C1=320, in_f32=False, seed=143),
+    "gn_cluster_48x48_c1280": lambda: case_groupnorm(N=1, H=48, W=48, C1=1280, seed=144),
+    "gn_cluster_batch_invariant": lambda: case_groupnorm_shapes_agree(seed=145, N=5, H=64, W=64, C1=320, C2=320),
     "ln_f32_320": lambda: case_layernorm(),
     "ln_bf16_1280": lambda: case_layernorm(rows=333, C=1280, in_f32=False, seed=42),
     "softmax_rows": lambda: case_softmax_rows(),
