@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(512, IN_F32 ? 2 : 1) gn_apply_kernel(const GnP
 // grid = (groups, N), NT = 256 threads, dynamic smem = HW * cpg * sizeof(input element).  (Tried and NOT kept: slices up to
 // 200 KB with 512 threads, one block per SM -- the VAE's 64x64 x 512 bf16 level took 65.6 us against 33.2 us for the
 // two-pass kernels at 8 images, profiles/r02_gn_onepass_experiment.txt; the UNet's 64x64 x 320 level has 10 channels per
-// group, which the 4-channel items of this kernel do not tile, so it stays two-pass either way.)
+// group, which the 4-channel items of this kernel do not tile, so it stays two-pass either way; a cluster-of-8 one-pass
+// kernel for that level was built and measured too -- 70 us against 53.6 us at batch 16, profiles/r02_gn_cluster_experiment.txt.)
 template <bool IN_F32, int NT>
 __global__ void __launch_bounds__(NT) gn_fused_small_kernel(const GnParams p) {
     pdl_trigger();
@@ -363,179 +364,6 @@ __global__ void __launch_bounds__(NT) gn_fused_small_kernel(const GnParams p) {
         }
         *reinterpret_cast<uint2*>(p.y + o) = make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
     }
-}
-
-// ---------------------------------------------------------------------------------------------- one-pass GroupNorm, clusters
-// The 64x64 level of the UNet: the (image, group) slices are too large for one block's shared memory and their 10 / 20
-// channels do not tile 16-byte items, so the two-pass kernels above read the level twice (3.6 TB/s at batch 16, 14 us for
-// two launches at batch 2).  Here a CLUSTER of CS blocks owns (image, block of CB channels = whole groups, a multiple of 16
-// channels so that rows of the bf16 output are 32-byte aligned): block r keeps pixels [r * ppc, (r + 1) * ppc) x CB channels
-// in shared memory while it accumulates them (thread = 8 consecutive channels, as above), the per-group (sum, sumsq) pairs
-// of the CS blocks are exchanged through distributed shared memory and combined in rank order in fp64 by every block,
-// and the block normalises its pixels from shared memory: one launch, one read of x, no global workspace, no atomics.
-// Deterministic and batch-invariant by construction (the geometry is a function of (HW, C, groups, dtype) only).
-struct GnClusterGeom { int cb; int cs; int ppc; int tpr; int rpb; size_t smem; };
-constexpr int kGnClusterMaxGroups = 16;                 // groups per channel block
-constexpr int kGnClusterMaxCS = 8;
-
-template <bool IN_F32>
-__global__ void __launch_bounds__(512) gn_cluster_kernel(const GnParams p, const int cb, const int ppc) {
-    pdl_trigger();
-    extern __shared__ __align__(16) unsigned char s_tile[];        // [ppc][cb] input elements, then the reduction scratch
-    __shared__ float s_xch[kGnClusterMaxCS][kGnClusterMaxGroups * 2];   // [source rank][group][sum, sumsq]
-    __shared__ float s_stat[kGnClusterMaxGroups * 2];              // [group][mean, rstd]
-    const int cs = (int)gridDim.x / (p.C / cb);                    // cluster size (runtime launch attribute)
-    const uint32_t rank = cluster_ctarank();
-    const int cblock = blockIdx.x / cs, n = blockIdx.y;
-    const int tpr = cb / 8, rpb = blockDim.x / tpr;                // threads per pixel row, rows in flight
-    const int tc = threadIdx.x % tpr, tr = threadIdx.x / tpr;
-    const bool live = tr < rpb;
-    const int c0 = cblock * cb + tc * 8;                           // first of this thread's 8 channels
-    const int gpb = cb / p.cpg;                                    // groups per channel block
-    const long long p0 = (long long)rank * ppc;
-    long long p1 = p0 + ppc;
-    if (p1 > p.HW) p1 = p.HW;
-    constexpr int VB = IN_F32 ? 32 : 16;                           // bytes of a thread's 8 channels
-    float s[8], ss[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
-    // ---- the block's tile comes in as one bulk copy per pixel row (cb contiguous channels, >= 160 bytes, 16-byte aligned):
-    // every byte of the tile is in flight at once -- register-staged loads (4 x 32 B per thread) kept 40 KB in flight per
-    // SM, i.e. ~40 GB/s per SM at 1 us of latency, and the kernel was no faster than the two-pass pair
-    __shared__ __align__(8) uint64_t s_bar;
-    const int rows = p1 > p0 ? (int)(p1 - p0) : 0;
-    const uint32_t row_bytes = (uint32_t)cb * (IN_F32 ? 4 : 2);
-    if (threadIdx.x == 0) {
-        mbar_init(&s_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    pdl_wait();
-    if (threadIdx.x == 0) mbar_expect_tx(&s_bar, (uint32_t)rows * row_bytes);    // (rows == 0: completes at once)
-    __syncthreads();
-    {
-        const bool blk_first = cblock * cb < p.C1;                     // a channel block never straddles the two sources
-        const unsigned char* base = reinterpret_cast<const unsigned char*>(blk_first ? p.x1 : p.x2);
-        const int Cb = blk_first ? p.C1 : p.C2, cb0 = blk_first ? cblock * cb : cblock * cb - p.C1;
-        for (int r = threadIdx.x; r < rows; r += blockDim.x) {
-            const unsigned char* gsrc = base + (((long long)n * p.HW + p0 + r) * Cb + cb0) * (IN_F32 ? 4 : 2);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(s_tile + (size_t)r * row_bytes)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(row_bytes),
-                           "r"(smem_u32(&s_bar)) : "memory");
-        }
-    }
-    mbar_wait(&s_bar, 0);
-    if (live) {
-        constexpr int U = 4;
-        for (int r = tr; r < rows; r += U * rpb) {               // pixel order per thread, as in the two-pass kernels
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int rr = r + u * rpb;
-                if (rr < rows) {
-                    const unsigned char* srcv = s_tile + ((size_t)rr * tpr + tc) * VB;
-                    Raw8<IN_F32> raw;
-                    raw.a = *reinterpret_cast<const uint4*>(srcv);
-                    if constexpr (IN_F32) raw.b = *reinterpret_cast<const uint4*>(srcv + 16);
-                    float v[8];
-                    unpack8<IN_F32>(raw, v);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { s[i] += v[i]; ss[i] += v[i] * v[i]; }
-                }
-            }
-        }
-    }
-    // block reduction in a fixed order: thread partials -> channel sums (rows added in row order) -> group sums
-    float* red = reinterpret_cast<float*>(s_tile + (size_t)ppc * cb * (IN_F32 ? 4 : 2));     // [rpb][tpr][16], then [cb][2]
-    if (live) {
-        float* mine = red + ((size_t)tr * tpr + tc) * 16;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { mine[i] = s[i]; mine[8 + i] = ss[i]; }
-    }
-    __syncthreads();
-    float* chan = red + (size_t)rpb * tpr * 16;
-    const int row_words = tpr * 16;
-    for (int o = threadIdx.x; o < row_words; o += blockDim.x) {
-        float a = 0.f;
-        for (int r = 0; r < rpb; ++r) a += red[(size_t)r * row_words + o];
-        const int k = o & 15;
-        chan[((o >> 4) * 8 + (k & 7)) * 2 + (k >> 3)] = a;
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < gpb * 2) {                              // thread (g, which): the group's channels added in order
-        const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
-        float a = 0.f;
-        for (int c = g * p.cpg; c < (g + 1) * p.cpg; ++c) a += chan[c * 2 + which];
-        const uint32_t slot = smem_u32(&s_xch[rank][g * 2 + which]);
-        for (int r = 0; r < cs; ++r)                               // every block of the cluster gets this block's partial
-            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(mapa_shared(slot, (uint32_t)r)), "f"(a) : "memory");
-    }
-    cluster_sync_all();                                            // release / acquire: the partials of all ranks are visible
-    if ((int)threadIdx.x < gpb) {
-        const int g = threadIdx.x;
-        double sum = 0.0, sq = 0.0;
-        for (int r = 0; r < cs; ++r) { sum += (double)s_xch[r][g * 2]; sq += (double)s_xch[r][g * 2 + 1]; }
-        const double inv_cnt = 1.0 / ((double)p.cpg * (double)p.HW);
-        const double m = sum * inv_cnt;
-        const double var = fmax(sq * inv_cnt - m * m, 0.0);
-        s_stat[g * 2] = (float)m;
-        s_stat[g * 2 + 1] = (float)(1.0 / sqrt(var + (double)p.eps));
-    }
-    __syncthreads();
-    if (live) {
-        float sc[8], sh[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = c0 + i, gl = (tc * 8 + i) / p.cpg;
-            sc[i] = s_stat[gl * 2 + 1] * p.gamma[c];
-            sh[i] = p.beta[c] - s_stat[gl * 2] * sc[i];
-        }
-        for (long long pix = p0 + tr; pix < p1; pix += rpb) {
-            const unsigned char* srcv = s_tile + ((size_t)(pix - p0) * tpr + tc) * VB;
-            Raw8<IN_F32> raw;
-            raw.a = *reinterpret_cast<const uint4*>(srcv);
-            if constexpr (IN_F32) raw.b = *reinterpret_cast<const uint4*>(srcv + 16);
-            float v[8];
-            unpack8<IN_F32>(raw, v);
-            const long long o = ((long long)n * p.HW + pix) * p.C + c0;
-            if (p.raw) {
-                *reinterpret_cast<uint4*>(p.raw + o) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                                   pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float y = v[i] * sc[i] + sh[i];
-                v[i] = p.silu ? silu_f(y) : y;
-            }
-            *reinterpret_cast<uint4*>(p.y + o) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                             pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-        }
-    }
-    // (no second cluster barrier: peers only WRITE into this block's s_xch, and all of those writes happen before the
-    //  barrier above)
-}
-
-// geometry of the cluster kernel for this call, or cs == 0 when it does not apply (-> two-pass kernels)
-static GnClusterGeom gn_cluster_geom(const rg_gn_t* g) {
-    GnClusterGeom z = {0, 0, 0, 0, 0, 0};
-    const int C = g->C1 + g->C2;
-    if (C % g->groups) return z;
-    const int cpg = C / g->groups;
-    const bool f32 = g->in_dtype == RG_DT_F32;
-    if (g->HW <= 1024 || g->HW > 4096) return z;                  // below: the one-block kernel; above: streaming two-pass
-    if (C >= 512 && !f32) return z;                                // the VAE's 64x64 x 512 bf16 level stays two-pass (measured)
-    int cb = cpg;                                                  // smallest multiple of cpg that is a multiple of 16 channels
-    while (cb % 16) cb += cpg;
-    while (cb < 64 && C % (2 * cb) == 0 && g->C1 % (2 * cb) == 0) cb *= 2;
-    if (cb > 128 || cb / cpg > kGnClusterMaxGroups || C % cb || g->C1 % cb) return z;
-    const int cs = kGnClusterMaxCS;
-    const int ppc = (int)((g->HW + cs - 1) / cs);
-    const int tpr = cb / 8;
-    int rpb = 320 / tpr; if (rpb > 64) rpb = 64;
-    const size_t tile = (size_t)ppc * cb * (f32 ? 4 : 2);
-    const size_t smem = tile + ((size_t)rpb * tpr * 16 + (size_t)cb * 2) * sizeof(float);
-    if (smem > 200 * 1024) return z;
-    GnClusterGeom r = {cb, cs, ppc, tpr, rpb, smem};
-    return r;
 }
 
 constexpr size_t kGnFusedMaxSmem = 96 * 1024;        // two blocks per SM
@@ -796,36 +624,6 @@ extern "C" int rg_groupnorm(const rg_gn_t* g, rg_stream_t stream) {
         else launch_kernel<1>(gn_fused_small_kernel<false, 256>, dim3(fgrid), dim3(256), smem, st, p);
         count_launch();
         return check_launch("gn_fused_small_kernel");
-    }
-    if (g && g->groups > 0 && g->HW > 0) {
-        const GnClusterGeom cg = gn_cluster_geom(g);
-        if (cg.cs > 0) {
-            GnParams p; dim3 grid; int threads;
-            memset(&p, 0, sizeof(p));
-            int rc = fill_gn(g, p, grid, threads);
-            if (rc) return rc;
-            if (!g->y) return set_error(RG_ERR_ARG, "groupnorm: null output");
-            static std::atomic<bool> done_t[kMaxDevices], done_f[kMaxDevices];
-            if ((rc = ensure_smem_attr(reinterpret_cast<const void*>(&gn_cluster_kernel<true>), 200 * 1024, done_t, "cudaFuncSetAttribute(gn_cluster_kernel)"))) return rc;
-            if ((rc = ensure_smem_attr(reinterpret_cast<const void*>(&gn_cluster_kernel<false>), 200 * 1024, done_f, "cudaFuncSetAttribute(gn_cluster_kernel)"))) return rc;
-            cudaLaunchConfig_t cfg;
-            memset(&cfg, 0, sizeof(cfg));
-            cfg.gridDim = dim3((unsigned)(cg.cs * (p.C / cg.cb)), (unsigned)p.N);
-            cfg.blockDim = dim3((unsigned)(cg.tpr * cg.rpb));
-            cfg.dynamicSmemBytes = cg.smem;
-            cfg.stream = reinterpret_cast<cudaStream_t>(stream);
-            cudaLaunchAttribute at[2];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = (unsigned)cg.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[1].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = at;
-            cfg.numAttrs = pdl_enabled(1) ? 2 : 1;
-            if (p.in_f32) cudaLaunchKernelEx(&cfg, gn_cluster_kernel<true>, p, cg.cb, cg.ppc);
-            else cudaLaunchKernelEx(&cfg, gn_cluster_kernel<false>, p, cg.cb, cg.ppc);
-            count_launch();
-            return check_launch("gn_cluster_kernel");
-        }
     }
     int rc = rg_groupnorm_stats(g, stream);
     if (rc) return rc;

@@ -586,7 +586,7 @@ CASES = {
     "gn_64x64_c320_f32_n2": lambda: case_groupnorm(N=2, H=64, W=64, C1=320, seed=38),
     "gn_64x64_concat640_bf16_n3": lambda: case_groupnorm(N=3, H=64, W=64, C1=320, C2=320, in_f32=False, raw=True, seed=39),
     "gn_32x32_concat1280_f32_n2": lambda: case_groupnorm(N=2, H=32, W=32, C1=640, C2=640, raw=True, seed=40),
-    # --- one-pass cluster kernel (64x64 level: 8 blocks per (image, 80-channel block), partials through DSMEM)
+    # --- more 64x64-level shapes (written for the cluster one-pass experiment, kept for the two-pass kernels)
     "gn_cluster_concat640_f32_raw": lambda: case_groupnorm(N=2, H=64, W=64, C1=320, C2=320, raw=True, seed=141),
     "gn_cluster_ragged_62x41": lambda: case_groupnorm(N=3, H=62, W=41, C1=320, silu=False, seed=142),
     "gn_cluster_c320_bf16_n16": lambda: case_groupnorm(N=16, H=64, W=64, C1=320, in_f32=False, seed=143),
