@@ -51,6 +51,8 @@ struct AttnParams {
     int heads, n_qpairs, n_items;
     float scale_log2;     // scale * log2(e)
     long long* trace;     // debug only (rg_debug_attn_trace): per-tile clock64 stamps of CTA 0, else nullptr
+    int turns;            // the two softmax warps of every SM sub-partition take turns for their exponential phases
+    int trace_item;       // which of CTA 0's work items is traced (rg_debug_attn_trace_item; default the first)
     int n_issuers;        // 1: warp 9 issues for both query tiles; 2: warp 9 -> tile 0, warp 11 -> tile 1
     int skew;             // cycles by which tile 1 starts behind tile 0 at a CTA's first work item (2 issuers only)
 };
@@ -78,7 +80,7 @@ struct AttnCfg {
     static constexpr int STAGE_BYTES = K_BYTES + V_BYTES;
     static constexpr int TILE_BYTES = 2 * Q_TILE_BYTES + STAGES * STAGE_BYTES;
     // barriers live behind the tiles; there is no static shared memory, so the dynamic window starts 1024-aligned
-    static constexpr int SMEM_BYTES = TILE_BYTES + 256;
+    static constexpr int SMEM_BYTES = TILE_BYTES + 512;
     static constexpr int O_STRIDE = (DV + 31) / 32 * 32;
     // TMEM columns: S_t[buf] at (t*SBUF+buf)*BKV.  PSEP: P_t has its own BKV/2 columns (two bf16 per column), so
     // S_t(G+SBUF) can be issued as soon as S_t(G) is in registers and runs under the softmax of tile G; otherwise P_t
@@ -87,9 +89,9 @@ struct AttnCfg {
     static constexpr int P_STRIDE = PSEP ? BKV / 2 : 0;
     static constexpr int O_COL = P_COL + 2 * P_STRIDE;
     static constexpr int TMEM_COLS = 512;
-    static constexpr int NBAR = 2 + 4 * SBUF + 4 + 3 * STAGES;
+    static constexpr int NBAR = 2 + 4 * SBUF + 4 + 3 * STAGES + 8;
     static_assert(O_COL + 2 * O_STRIDE <= 512, "TMEM budget");
-    static_assert(NBAR * 8 + 8 + 16 <= 256, "barrier area");
+    static_assert(NBAR * 8 + 8 + 16 <= 512, "barrier area");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(BKV == 64 || BKV == 128, "BKV");
     static_assert(SBUF == 1 || SBUF == 2, "SBUF");
@@ -97,6 +99,18 @@ struct AttnCfg {
     static_assert(!PSEP || STAGES >= SBUF + 1, "SBUF tiles of score look-ahead need SBUF+1 K/V stages");
 };
 
+#ifndef RG_ATTN_SETMAXNREG
+#define RG_ATTN_SETMAXNREG 1
+#endif
+#ifndef RG_ATTN_EXP_F32
+#define RG_ATTN_EXP_F32 0
+#endif
+// Register budget by role (setmaxnreg, per warpgroup): the helper warpgroup (warps 8-11: one or zero active threads each)
+// gives registers back so that the softmax warpgroups keep S (128 fp32), P (64 packed pairs) and the exponentials in
+// flight without spills: 2 x 128 x kSoftmaxRegs + 128 x kHelperRegs <= 64 K.  The instruction must dominate the role's
+// code (ptxas budgets registers per region), hence the two-level role dispatch in the kernel.
+constexpr int kSoftmaxRegs = 232, kHelperRegs = 40;
+static_assert(256 * kSoftmaxRegs + 128 * kHelperRegs <= 65536, "register file");
 constexpr int kAttnThreads = 384;
 // Stagger (cycles) of query tile 1 behind tile 0 for the long key loops: the two warps that share an SM sub-partition
 // then run their exponential phase (MUFU-bound) and their bookkeeping (barrier round trips, tcgen05.ld / st, row max:
@@ -127,8 +141,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     uint64_t* pv_done = p_full + 2;                    // [t]       O_t += P_t(G) V retired         (tensor core -> softmax)
     uint64_t* kv_full = pv_done + 2; uint64_t* kv_empty = kv_full + STAGES;
     uint64_t* kv_land = kv_empty + STAGES;             // [stage]   fp16: TMA bytes landed (-> patch warp -> kv_full)
-    uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(kv_land + STAGES);
-    volatile long long* t0_stamp = reinterpret_cast<volatile long long*>(kv_land + STAGES + 1);   // [item parity] clock64 of warpgroup 0's start
+    uint64_t* exp_done = kv_land + STAGES;             // [sub-partition q][t] warp q of warpgroup t has issued its exponentials of tile G
+    uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(exp_done + 8);
+    volatile long long* t0_stamp = reinterpret_cast<volatile long long*>(exp_done + 8 + 1);   // [item parity] clock64 of warpgroup 0's start
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kv = (p.Nk + BKV - 1) / BKV;
@@ -140,6 +155,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         for (int i = 0; i < 2 * SBUF; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128); }
         for (int t = 0; t < 2; ++t) { mbar_init(&p_full[t], 128); mbar_init(&pv_done[t], 1); }
         for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], p.n_issuers); mbar_init(&kv_land[s], 1); }
+        for (int i = 0; i < 8; ++i) mbar_init(&exp_done[i], 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&tmem_base_smem, Cfg::TMEM_COLS);
@@ -149,6 +165,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     const uint32_t tmem_base = tmem_base_smem;
     pdl_wait();                         // prologue above overlapped the previous kernel
 
+    if (warp >= 8) {
+#if RG_ATTN_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kHelperRegs));
+#endif
     if (warp == 8) {
         // ===================================================================== TMA producer
         if (lane == 0) {
@@ -257,6 +277,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
             // picked up ITS first score tile (warp 0 stamps clock64 before its s_free arrival; the barrier is only polled
             // here, warpgroup 0's own issuer consumes it): warpgroup 1 then runs that far behind warpgroup 0 through the
             // item's key loop, whatever happened at the item boundary
+            // ... and tile 0's issuer starts an item only when warpgroup 1 has published the last P of the previous one
+            // (p_full[1] is only polled here; tile 1's issuer consumes it).  Without this the offset is free to grow item
+            // by item until warpgroup 1 runs exactly one step behind -- lock-step again, measured with the fp32
+            // exponentials: skew 1200 cycles in a CTA's first item, 3300 = one full step in its seventh.
+            auto rephase = [&](uint32_t g0_, uint32_t it_) {
+                if (PSEP && two && t_lo == 0 && p.skew > 0 && it_ > 0) mbar_wait(&p_full[1], (g0_ - 1) & 1);
+            };
             auto stagger = [&](uint32_t g0_, uint32_t it_) {
                 if (PSEP && two && t_lo == 1 && p.skew > 0) {          // (s_free / t0_stamp exist for separate P columns only)
                     mbar_wait(&s_free[g0_ % SBUF], (g0_ / SBUF) & 1);      // warpgroup 0 has started the item's first tile ...
@@ -268,6 +295,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it, g0 += n_kv) {
                 mbar_wait(&q_full, it & 1);
                 tc_fence_after();
+                rephase(g0, it);
                 if constexpr (!PSEP) {
                     wait_kv(g0);
                     stagger(g0, it);
@@ -305,8 +333,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                 }
             }
         }
+    }
     } else {
         // ===================================================================== softmax warpgroups
+#if RG_ATTN_SETMAXNREG
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSoftmaxRegs));
+#endif
         const int t = warp >> 2, qd = warp & 3;
         const int row = qd * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
@@ -319,7 +351,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
             const int qp = item % p.n_qpairs, bh = item / p.n_qpairs;
             const int h = bh % p.heads, b = bh / p.heads;
             float m_run = -INFINITY, l_run = 0.f;
-            long long* tr = (p.trace && blockIdx.x == 0 && lane == 0 && g0 == 0) ? p.trace : nullptr;
+            long long* tr = (p.trace && blockIdx.x == 0 && lane == 0 && (int)it_s == p.trace_item) ? p.trace : nullptr;
             for (int j = 0; j < n_kv; ++j) {
                 const uint32_t G = g0 + j;
                 RG_STAMP(0);
@@ -393,6 +425,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                 if constexpr (PSEP && kAttnPStream) {            // P_t's own columns: free once O_t += P_t(G-1) V has retired,
                     if (!quiescent) { mbar_wait(&pv_done[t], (G - 1) & 1); tc_fence_after(); quiescent = true; }   // long ago by now
                 }
+                // Turn-taking (p.turns, off by default -- measured slower than the stagger, see launch_attn): this warp and the
+                // other softmax warp of its SM sub-partition (same quarter qd, other warpgroup) never run their exponentials
+                // together -- warpgroup 0's tile G, then warpgroup 1's tile G, then warpgroup 0's tile G + 1 ...
+                if (p.turns) {
+                    if (t == 0) { if (G > 0) mbar_wait(&exp_done[qd * 2 + 1], (G - 1) & 1); }
+                    else mbar_wait(&exp_done[qd * 2 + 0], G & 1);
+                }
                 const float neg_m = -m_run;
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
                 uint32_t pk[BKV / 2];
@@ -400,10 +439,19 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                     // two exponentials per MUFU instruction on the packed logits; the row sum comes out of the P V GEMM
 #pragma unroll
                     for (int i = 0; i < BKV; i += 2) {
+#if RG_ATTN_EXP_F32
+                        // (-DRG_ATTN_EXP_F32=1, not the default.)  ex2.approx.f16x2 is two MUFU.EX2.F16 plus a PRMT, fed by a
+                        // conversion: 6 instructions per pair in a chain.  Two fp32 exponentials and ONE packing conversion are
+                        // 5 and the SASS is a clean MUFU, MUFU, F2FP stream: 2650 cycles per step instead of 2890 while the
+                        // warpgroups stay half a step apart -- but with this form they drift into lock-step (3350 cycles).
+                        const float e0 = ex2_approx(fmaf(s[i], sl, neg_m)), e1 = ex2_approx(fmaf(s[i + 1], sl, neg_m));
+                        pk[i / 2] = pack_f16x2(e0, e1);
+#else
                         const float x0 = fmaf(s[i], sl, neg_m), x1 = fmaf(s[i + 1], sl, neg_m);
                         uint32_t h;
                         asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
                         asm("ex2.approx.f16x2 %0, %1;" : "=r"(pk[i / 2]) : "r"(h));
+#endif
                         if ((!PSEP || kAttnPStream) && (i & 31) == 30)             // stream each finished 32-key chunk out
                             tmem_st16(p_tmem + (i - 30) / 2, reinterpret_cast<uint32_t (&)[16]>(pk[(i - 30) / 2]));
                     }
@@ -420,6 +468,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
                         if ((!PSEP || kAttnPStream) && (i & 31) == 28)             // stream each finished 32-key chunk out
                             tmem_st16(p_tmem + (i - 28) / 2, reinterpret_cast<uint32_t (&)[16]>(pk[(i - 28) / 2]));
                     }
+                }
+                if (p.turns) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&exp_done[qd * 2 + t]);
                 }
                 RG_STAMP(4);
                 if constexpr (PSEP && !kAttnPStream) {
@@ -479,6 +531,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
 }
 
 static long long* g_attn_trace = nullptr;
+static int g_attn_trace_item = 0;
 
 static int encode_qkv_map(CUtensorMap* m, const void* base, int d, int heads, long long tokens, int B, long long sh,
                           long long st, long long sb, int rows) {
@@ -512,13 +565,20 @@ static int launch_attn(const rg_attn_t* a, cudaStream_t stream) {
     p.n_items = (int)items;
     p.scale_log2 = a->scale * 1.4426950408889634f;
     p.trace = g_attn_trace;
+    p.trace_item = g_attn_trace_item;
     // long key loops: one issuer per warpgroup and the warpgroups half a period apart; short ones (cross attention, the
     // few-token levels) are latency-bound chains where a second issuer only adds contention (profiles/r02_attn_variants.txt)
     p.n_issuers = (PSEP && (a->Nk + BKV - 1) / BKV >= 8) ? 2 : 1;
+    // Measured on the 4096-token launch (profiles/r02_attn_variants.txt): stagger 734 us; strict turn-taking of the
+    // exponential phases 770 us with the fp32 exponentials (a lone warp needs ~1400 cycles per tile, so 2 x 1500 per step)
+    // and 883 us with the f16x2 form; fp32 exponentials + stagger 840 us (2650 cycles per step while the offset holds,
+    // but the warpgroups drift into lock-step within an item).
+    p.turns = 0;
     p.skew = p.n_issuers == 2 ? kAttnSkewCycles : 0;
 #ifdef RG_ATTN_TUNING            /* perf experiments only: never in the product build */
     { const char* e = getenv("RG_ATTN_ISSUERS"); if (e) p.n_issuers = atoi(e) == 2 ? 2 : 1; }
     { const char* e = getenv("RG_ATTN_SKEW"); if (e) p.skew = p.n_issuers == 2 ? atoi(e) : 0; }
+    { const char* e = getenv("RG_ATTN_TURNS"); if (e) p.turns = (p.n_issuers == 2 && atoi(e)) ? 1 : 0; }
 #endif
     const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
     launch_kernel(attention_kernel<DKA, DQK, DV, BKV, SBUF, PSEP, STAGES, F16, CAUSAL>, dim3(grid), dim3(kAttnThreads), Cfg::SMEM_BYTES, stream, p);
@@ -533,6 +593,7 @@ using namespace rg;
 // Debug hook (not part of the public header): device buffer of 8 warps x 64 tiles x 8 clock64 stamps written by
 // CTA 0 for its first work item; nullptr switches tracing off.
 extern "C" void rg_debug_attn_trace(void* dev_buf) { g_attn_trace = reinterpret_cast<long long*>(dev_buf); }
+extern "C" void rg_debug_attn_trace_item(int item) { g_attn_trace_item = item; }
 
 extern "C" int rg_attention(const rg_attn_t* a, rg_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

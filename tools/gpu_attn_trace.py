@@ -18,6 +18,9 @@ qkv = torch.randn((16, N, 3, 8, d), device="cuda").to(dt)
 buf = torch.zeros((18, 64, 8), dtype=torch.int64, device="cuda")
 ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], d ** -0.5)
 lib.rg_debug_attn_trace.argtypes = [__import__("ctypes").c_void_p]
+if len(sys.argv) > 4:                 # which of CTA 0's work items to trace (default: its first)
+    lib.rg_debug_attn_trace_item.argtypes = [__import__("ctypes").c_int]
+    lib.rg_debug_attn_trace_item(int(sys.argv[4]))
 lib.rg_debug_attn_trace(buf.data_ptr())
 ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], d ** -0.5)
 torch.cuda.synchronize()
