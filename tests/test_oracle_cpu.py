@@ -288,3 +288,17 @@ def test_weight_packing_identities():
     # units of 32 rows: 16 value rows followed by their 16 gate rows (GEMM epilogue, csrc/gemm.cu)
     assert bi[:16].tolist() == list(range(16)) and bi[16:32].tolist() == list(range(320, 336))
     assert bi[32:48].tolist() == list(range(16, 32)) and torch.equal(wi[:, 0], bi)
+
+
+def test_operand_dtype_selection_is_per_process():
+    """RESTORAGEN_OPERAND_DTYPE picks the library and the host modules' 16-bit dtype at import (fp16 parity mode)."""
+    import os, subprocess, sys
+    code = ("from image_restoration_and_enhancement_b200 import _lib, ops; "
+            "print(_lib.LIB_PATH.name, ops.OPERAND_DTYPE, _lib.load().rg_operand_dtype())")
+    for env, want in (("", "librestoragen.so torch.bfloat16 0"), ("fp16", "librestoragen_f16.so torch.float16 2")):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(ROOT),
+                           env=dict(os.environ, RESTORAGEN_OPERAND_DTYPE=env))
+        assert r.returncode == 0 and r.stdout.strip().splitlines()[-1] == want, (r.stdout, r.stderr[-500:])
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(ROOT),
+                       env=dict(os.environ, RESTORAGEN_OPERAND_DTYPE="int8"))
+    assert r.returncode != 0 and "RESTORAGEN_OPERAND_DTYPE" in r.stderr
