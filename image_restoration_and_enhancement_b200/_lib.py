@@ -37,7 +37,7 @@ class RgConv(C.Structure):
                 ("out_bf16", C.c_void_p), ("out_f32", C.c_void_p),
                 ("out_stride_n", C.c_int64), ("out_stride_h", C.c_int64), ("out_stride_w", C.c_int64),
                 ("act", C.c_int32), ("scale", C.c_float), ("out16_dtype", C.c_int32),
-                ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64)]
+                ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64), ("parities", C.c_int32)]
 
 
 class RgAttn(C.Structure):

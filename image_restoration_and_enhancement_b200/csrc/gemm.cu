@@ -70,6 +70,10 @@ struct GemmParams {
     int out_f16;                      // the 16-bit output is fp16 (attention operands), not bf16
     int out_cols;                     // Cout, or Cout / 2 for GEGLU
     CUtensorMap resmap, pmap, hmap;   // residual load, primary store, secondary (bf16) store
+    // parity-split upsample in one launch (rg_conv_t::parities == 4): column tiles [par * tiles_per_par, ..) belong to output
+    // parity par = 2 py + px: its taps are shifted by (px, py) and its boxes go through its own strided view of the output
+    int n_par, tiles_per_par;
+    CUtensorMap pmap_par[3];          // primary store maps of parities 1..3 (parity 0: pmap)
 };
 
 // warp 0 TMA, warp 1 MMA, warps 2..EW+1 epilogue (EW / 4 per TMEM lane quarter).  EW = 8 for main-loop-bound shapes
@@ -199,13 +203,16 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
         if (n_row >= p.N) n_row = p.N - 1;                // padding rows: any valid image (their result is clipped)
         const float* const bn_row = use_bn ? p.bias_n + (long long)n_row * p.bias_n_ld : nullptr;
         const float* const bias_t = bias;
+        const int par = p.n_par > 1 ? n_tile / p.tiles_per_par : 0;          // parity-split upsample: this tile's output view
+        const int n_loc = n_tile - par * p.tiles_per_par;
+        const CUtensorMap* const pm = par ? &p.pmap_par[par - 1] : &p.pmap;
 #pragma unroll 1
         for (int c = 0; c < NC; ++c) {
             const uint32_t slot = (cc + c) % Cfg::SLOTS, use = (cc + c) / Cfg::SLOTS;
             mbar_wait(&acc_full[slot], use & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)row0 << 16) + slot * BNC;
-            const int gcol0 = n_tile * Cfg::N_TILE + c * BNC;
+            const int gcol0 = n_loc * Cfg::N_TILE + c * BNC;
 #pragma unroll 1
             for (int k = 0; k < CNT && !skip_units; ++k, ++A) {
                 const int u = part + PARTS * k;
@@ -307,7 +314,7 @@ __device__ __noinline__ void epilogue_tma(const GemmParams& p, uint8_t* staging,
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0 && !skip_store) {
-                    if (prim_store) tma_store_4d(&p.pmap, pb, ocol, cw, ch, cn);
+                    if (prim_store) tma_store_4d(pm, pb, ocol, cw, ch, cn);
                     if (sec_store) tma_store_4d(&p.hmap, hb, ocol, cw, ch, cn);
                     bulk_commit();
                 }
@@ -567,10 +574,12 @@ __device__ __noinline__ void cluster_splitk_final(const GemmParams& p, const uin
     const float* const bias = p.bias;
     const float* const bias_n = p.bias_n;
     const void* const res = p.res;
-    const CUtensorMap* const pmap = &p.pmap;
-    const CUtensorMap* const hmap = &p.hmap;
+        const CUtensorMap* const hmap = &p.hmap;
     auto pack16 = [&](float lo, float hi) { return out_f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); };
-    const int mp = t2 / n_tiles_n, n_tile = t2 - mp * n_tiles_n;
+    const int mp = t2 / n_tiles_n, n_tile_g = t2 - mp * n_tiles_n;
+    const int par = p.n_par > 1 ? n_tile_g / p.tiles_per_par : 0;          // parity-split upsample: this tile's output view
+    const int n_tile = n_tile_g - par * p.tiles_per_par;
+    const CUtensorMap* const pmap = par ? &p.pmap_par[par - 1] : &p.pmap;
     const int m_tile = 2 * mp + (int)rank;
     const int twi = m_tile % tiles_w;
     const int rest = m_tile / tiles_w;
@@ -684,6 +693,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         for (int i = 0; i < 5; ++i) tma_prefetch_desc(&p.amap[i]);
         tma_prefetch_desc(&p.bmap);
         if (p.epi_tma) { tma_prefetch_desc(&p.resmap); tma_prefetch_desc(&p.pmap); tma_prefetch_desc(&p.hmap); }
+        if (p.n_par > 1) for (int i = 0; i < 3; ++i) tma_prefetch_desc(&p.pmap_par[i]);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -719,7 +729,8 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
                 const int twi = m_tile % p.tiles_w;
                 const int rest = m_tile / p.tiles_w;
                 const int thi = rest % p.tiles_h, tni = rest / p.tiles_h;
-                const int w0 = twi * TW, h0 = thi * TH, n0 = tni * (128 >> (p.lw + p.lh));   // n0 >= N: zero fill
+                const int par = p.n_par > 1 ? n_tile / p.tiles_per_par : 0;                  // output parity of this column tile
+                const int w0 = twi * TW + (par & 1), h0 = thi * TH + (par >> 1), n0 = tni * (128 >> (p.lw + p.lh));   // n0 >= N: zero fill
                 const int brow = n_tile * Cfg::N_TILE + (int)rank * (BNC / 2);
                 const int kb0 = ks * p.kper, kb1 = kb0 + p.kper < p.total_kblk ? kb0 + p.kper : p.total_kblk;
                 int kblk = 0;
@@ -1028,6 +1039,9 @@ static int launch_gemm(GemmParams& gp, const void* w, long long ktot, long long 
     }
     gp.n_tiles_n = (gp.Cout + Cfg::N_TILE - 1) / Cfg::N_TILE;
     if (gp.Cout % Cfg::N_TILE != 0) gp.epi_tma = 0;        // the TMA epilogue assumes every 16-column unit is real
+    gp.tiles_per_par = gp.n_tiles_n / (gp.n_par > 1 ? gp.n_par : 1);
+    if (gp.n_par > 1 && (!gp.epi_tma || gp.n_tiles_n % gp.n_par != 0))
+        return set_error(RG_ERR_ARG, "rg_conv2d: parities = 4 needs Cout to be a multiple of the column tile");
     const int total = gp.n_pairs_m * gp.n_tiles_n * gp.ksplit;
     const int max_clusters = sm_count() / 2;
     const int clusters = total < max_clusters ? total : max_clusters;
@@ -1088,8 +1102,14 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
     if (c->x.stride_w % 8 || c->x.stride_h % 8 || c->x.stride_n % 8 || (reinterpret_cast<uintptr_t>(c->x.data) & 15))
         return set_error(RG_ERR_ARG, "rg_conv2d: x strides must be multiples of 8 elements, base 16-B aligned");
 
+    const bool parity4 = c->parities == 4;
+    if (c->parities != 0 && c->parities != 1 && !parity4) return set_error(RG_ERR_ARG, "rg_conv2d: parities must be 0, 1 or 4");
+    if (parity4 && (c->kh != 2 || c->kw != 2 || c->stride != 1 || c->has_x2 || c->res || c->bias_n || c->out_bf16 || !c->out_f32 ||
+                    c->act != RG_ACT_NONE || c->Cout % 160 != 0))
+        return set_error(RG_ERR_ARG, "rg_conv2d: parities = 4 is the 2x2 parity-split upsample: fp32 output, bias only, Cout % 160 == 0");
     GemmParams gp;
     memset(&gp, 0, sizeof(gp));
+    gp.n_par = parity4 ? 4 : 1;
     const int OW = c->OW, OH = c->OH, N = c->x.N;
     // spatial tile: TW x TH x TN = 128 output pixels
     int lw = ilog2_ceil(OW < 128 ? OW : 128);
@@ -1103,7 +1123,7 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
     gp.tiles_n = (N + TN - 1) / TN;
     const int n_tiles_m = gp.tiles_w * gp.tiles_h * gp.tiles_n;
     gp.n_pairs_m = (n_tiles_m + 1) / 2;          // an odd last 128-pixel tile is paired with an all-padding one
-    gp.N = N; gp.OH = OH; gp.OW = OW; gp.Cout = c->Cout;
+    gp.N = N; gp.OH = OH; gp.OW = OW; gp.Cout = parity4 ? 4 * c->Cout : c->Cout;      // rows of the weight matrix
 
     const int cblk = (c->x.C + 63) / 64;
     int n_items = 0, n_maps = 0, rc;
@@ -1114,7 +1134,8 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
         if (rc) return rc;
         n_maps = 1;
         for (int kh = 0; kh < c->kh; ++kh)
-            for (int kw = 0; kw < c->kw; ++kw) gp.items[n_items++] = GemmItem{0, kw - c->pad_l, kh - c->pad_t, cblk};
+            for (int kw = 0; kw < c->kw; ++kw)
+                gp.items[n_items++] = GemmItem{0, kw - (parity4 ? 1 : c->pad_l), kh - (parity4 ? 1 : c->pad_t), cblk};   // parity (py, px) adds (px, py) in the kernel
     } else {
         // four parity views: view (ph,pw) holds input pixels (2i+ph, 2j+pw)
         for (int ph = 0; ph < 2; ++ph)
@@ -1191,10 +1212,14 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
             const int bw = TW < 32 ? TW : 32;
             const int bh = TH < 32 / bw ? TH : 32 / bw;
             const int bn = 32 / (bw * bh);
-            auto enc = [&](CUtensorMap* m, const void* base, bool f32) -> int {
+            auto enc = [&](CUtensorMap* m, const void* base, bool f32, int par = 0) -> int {
                 const long long esz = f32 ? 4 : 2;
                 // extent-1 dimensions may come with a zero / arbitrary pitch: give them a sane one
                 long long sw = c->out_stride_w, sh = c->out_stride_h, sn = c->out_stride_n;
+                if (parity4) {                       // view of output parity (py, px): every second row / column of the full tensor
+                    base = reinterpret_cast<const char*>(base) + ((par >> 1) * sh + (par & 1) * sw) * esz;
+                    sw *= 2; sh *= 2;
+                }
                 if (OW == 1 && sw < gp.out_cols) sw = (gp.out_cols + 7) / 8 * 8;
                 if (OH == 1 && sh < sw * OW) sh = sw * OW;
                 if (N == 1 && sn < sh * OH) sn = sh * OH;
@@ -1207,6 +1232,9 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
             };
             const void* pout = prim_f32 ? (const void*)c->out_f32 : (const void*)c->out_bf16;
             if (gp.prim_store && (rc = enc(&gp.pmap, pout, prim_f32))) return rc;
+            if (parity4)
+                for (int par = 1; par < 4; ++par)
+                    if ((rc = enc(&gp.pmap_par[par - 1], pout, prim_f32, par))) return rc;
             if (c->res && (rc = enc(&gp.resmap, c->res, prim_f32))) return rc;
             if (gp.sec_store && (rc = enc(&gp.hmap, c->out_bf16, false))) return rc;
             if (!gp.prim_store) gp.pmap = c->res ? gp.resmap : gp.hmap;
@@ -1230,7 +1258,7 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
 
     // ---- tile shape.  Columns: one or two chunks of BNC.  The 2 x 160 tile halves the L2 traffic per FLOP but
     // quantises the grid more coarsely; estimate both (cycles per k-block: max(MMA, L2 fill at ~43 B/clk/SM)).
-    const int Cout = c->Cout;
+    const int Cout = gp.Cout;                    // weight rows (4 x Cout for the parity-split upsample)
     if (c->act == RG_ACT_GEGLU) {
         if (Cout % 32 != 0 || !c->out_bf16 || c->out_f32 || c->res || c->bias_n || !aligned)
             return set_error(RG_ERR_ARG, "rg_conv2d: GEGLU needs Cout % 32 == 0 and a 16-B aligned bf16 output only");
@@ -1272,7 +1300,7 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
                                 : launch_gemm<160, 1, 16, 2>(gp, c->w, ktot, w_ld, stream);
             }
         }
-        if (ks > 1) {
+        if (ks > 1 && gp.n_par == 1) {
             // 16 epilogue warps: 2-3 units per warp instead of 5 -- the fix-up of a tile is a serial chain of units in the
             // last-arriving warp (one L2 round trip each), so its depth is what the launch waits for
             using Cfg = GemmCfg<160, 1, 16>;
@@ -1302,7 +1330,8 @@ extern "C" int rg_conv2d(const rg_conv_t* c, rg_stream_t stream_) {
         { const char* e = getenv("RG_GEMM_NC2_MIN_KBLK"); if (e) min_kblk = atoi(e); }
         { const char* e = getenv("RG_GEMM_EW16_MAX_KBLK"); if (e) ew16 = atoi(e); }
 #endif
-        if (Cout % 320 == 0 && gp.total_kblk > min_kblk && (long long)waves(320) * 865 <= (long long)waves(160) * 625)
+        if (Cout % 320 == 0 && (!parity4 || c->Cout % 320 == 0) && gp.total_kblk > min_kblk &&
+            (long long)waves(320) * 865 <= (long long)waves(160) * 625)
             return launch_gemm<160, 2>(gp, c->w, ktot, w_ld, stream);
         if (gp.epi_tma && gp.total_kblk <= ew16) return launch_gemm<160, 1, 16>(gp, c->w, ktot, w_ld, stream);
         return launch_gemm<160, 1>(gp, c->w, ktot, w_ld, stream);

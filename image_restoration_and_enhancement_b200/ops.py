@@ -134,18 +134,20 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, *, kh: int = 1, kw: int = 1, stride
            bias: torch.Tensor | None = None, bias_n: torch.Tensor | None = None, res: torch.Tensor | None = None,
            out_bf16: torch.Tensor | bool | None = None, out_f32: torch.Tensor | bool | None = None,
            act: int = RG_ACT_NONE, scale: float = 1.0, out_strides: tuple | None = None, w_ld: int = 0,
-           out_half: torch.dtype = bf16):
+           out_half: torch.dtype = bf16, parities: int = 0):
     """Implicit-GEMM convolution / linear (rg_conv2d).  ``x``: bf16 [N,H,W,C]; ``w``: bf16 [Cout, kh*kw*C (+C2)].
 
     ``out_bf16`` / ``out_f32``: True to allocate a contiguous [N,OH,OW,Cout'] output, or a tensor to write into
     (with ``out_strides`` = element strides (n, h, w) when it is not contiguous).  ``out_half``: element type of the
     16-bit output (bf16, or fp16 for the attention operands).  Returns (out_bf16, out_f32).
+    ``parities=4``: the parity-split "nearest-2x upsample + 3x3 conv" in one launch -- ``w`` = [4 * Cout, 4 * C] (the four 2x2
+    kernels stacked in (py, px) order), OH x OW = the input grid, ``out_f32`` = the full [N, 2 OH, 2 OW, Cout] tensor.
     """
     lib = _lib.load()
     N, H, W, Cin = x.shape
     OH = H if OH is None else OH
     OW = W if OW is None else OW
-    Cout = w.shape[0]
+    Cout = w.shape[0] // 4 if parities == 4 else w.shape[0]
     ktot = kh * kw * Cin + (x2.shape[3] if x2 is not None else 0)
     assert w.dtype == bf16 and w.stride(1) == 1 and w.shape[1] == ktot, (w.shape, ktot)
     if w_ld == 0 and w.stride(0) != ktot:
@@ -159,6 +161,10 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, *, kh: int = 1, kw: int = 1, stride
         out_bf16 = None
     if out_f32 is False:
         out_f32 = None
+    if parities == 4:
+        assert isinstance(out_f32, torch.Tensor) and out_f32.shape == (N, 2 * OH, 2 * OW, Cout) and out_bf16 is None
+        if out_strides is None:
+            out_strides = (out_f32.stride(0), out_f32.stride(1), out_f32.stride(2))
     if out_strides is None:
         out_strides = (OH * OW * Cw, OW * Cw, Cw)
     p = RgConv()
@@ -185,12 +191,13 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, *, kh: int = 1, kw: int = 1, stride
         p.out_f32 = out_f32.data_ptr()
     p.out_stride_n, p.out_stride_h, p.out_stride_w = out_strides
     p.act, p.scale = act, scale
+    p.parities = parities
     if SPLITK:
         ws = _splitk_workspace(x.device)
         p.splitk_ws, p.splitk_ws_bytes = ws.data_ptr(), ws.numel()
     e0 = _prof_begin()
     check(lib.rg_conv2d(C.byref(p), _stream()), "rg_conv2d")
-    _prof_end(e0, 2.0 * N * OH * OW * Cout * ktot, "gemm",
+    _prof_end(e0, 2.0 * N * OH * OW * w.shape[0] * ktot, "gemm",
               f"conv{kh}x{kw}s{stride} M={N * OH * OW} ({N}x{OH}x{OW}) N={Cout} K={ktot} act={act}"
               f"{' res' if res is not None else ''}{' f32out' if out_f32 is not None else ''}")
     return out_bf16, out_f32

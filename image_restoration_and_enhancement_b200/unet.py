@@ -126,7 +126,8 @@ class UNetB200:
             if i < 3:
                 w = sd[f"up_blocks.{i}.upsamplers.0.conv.weight"]
                 bias = f(f"up_blocks.{i}.upsamplers.0.conv.bias")
-                blk["up"] = ([(py, px, wp.to(dev, bf16)) for py, px, wp in upsample_parity_weights(w)],
+                par = {(py, px): wp for py, px, wp in upsample_parity_weights(w)}
+                blk["up"] = (torch.cat([par[(py, px)] for py in (0, 1) for px in (0, 1)], dim=0).to(dev, bf16).contiguous(),
                              pack_conv(w).to(dev, bf16), bias)
             self.up.append(blk)
         self.w_temb = torch.cat(temb_w, dim=0).to(dev, bf16).contiguous()
@@ -204,11 +205,10 @@ class UNetB200:
             _, of = ops.conv2d(u, w_plain, kh=3, kw=3, pad_t=1, pad_l=1, bias=bias, out_f32=True)
             return of
         out = torch.empty((N, 2 * H, 2 * W, Cc), dtype=f32, device=xb.device)
-        sn, sh, sw = out.stride(0), out.stride(1), out.stride(2)
-        for py, px, wp in wts:
-            # parity (py,px): output pixels (2j+py, 2i+px) = 2x2 conv over rows {j-1+py, j+py}, cols {i-1+px, i+px}
-            ops.conv2d(xb, wp, kh=2, kw=2, pad_t=1 - py, pad_l=1 - px, OH=H, OW=W, bias=bias,
-                       out_f32=out[:, py:, px:], out_strides=(sn, 2 * sh, 2 * sw))
+        # parity (py,px): output pixels (2j+py, 2i+px) = 2x2 conv over rows {j-1+py, j+py}, cols {i-1+px, i+px}; the four
+        # kernels are stacked along Cout and run as ONE launch (rg_conv_t::parities = 4): at small batch each parity alone
+        # fills a fraction of the SMs and costs a whole launch of latency
+        ops.conv2d(xb, wts, kh=2, kw=2, OH=H, OW=W, bias=bias, out_f32=out, parities=4)
         return out
 
     # ------------------------------------------------------------------------------------------ forward

@@ -112,6 +112,12 @@ typedef struct rg_conv {
        least RG_SPLITK_WS_MIN_BYTES, and is shared by all calls of one stream. */
     void* splitk_ws;
     int64_t splitk_ws_bytes;
+    /* 0 / 1: an ordinary convolution.  4: the parity-split form of "nearest-2x upsample + 3x3 convolution" in ONE launch
+       (kh = kw = 2, stride 1, fp32 output only, no residual): w = bf16 [4][Cout][4 * x.C], the four 2x2 kernels of output
+       parities (py, px) = (0,0), (0,1), (1,0), (1,1) stacked along the rows; parity (py, px) reads input rows
+       {j-1+py, j+py} and columns {i-1+px, i+px} (pad_t / pad_l are ignored) and writes output pixel (2j+py, 2i+px);
+       OH x OW is the INPUT-resolution grid and out_f32 / out_stride_* address the full [N][2 OH][2 OW][Cout] tensor. */
+    int32_t parities;
 } rg_conv_t;
 
 #define RG_SPLITK_COUNTER_BYTES (256 * 1024)

@@ -224,6 +224,27 @@ def case_conv_strided_out(seed=29):
     return max(errs), TOL_F32
 
 
+def case_upsample_conv_one_launch(N=2, H=16, W=16, Cin=1280, Cout=1280, seed=150):
+    """rg_conv_t::parities = 4: nearest-2x upsample + 3x3 conv as ONE launch of the four stacked 2x2 parity kernels, against
+    F.interpolate + F.conv2d in fp32 (weights packed by the product's own upsample_parity_weights)."""
+    _setup()
+    from image_restoration_and_enhancement_b200.weights import upsample_parity_weights
+    x = _rand((N, H, W, Cin), seed)
+    w = _rand((Cout, Cin, 3, 3), seed + 1, 1.0 / math.sqrt(Cin * 9), torch.float32)
+    w = w.to(torch.bfloat16).float()
+    b = _rand((Cout,), seed + 2, 0.5, torch.float32)
+    par = {(py, px): wp for py, px, wp in upsample_parity_weights(w)}
+    wst = torch.cat([par[(py, px)] for py in (0, 1) for px in (0, 1)], dim=0).to(torch.bfloat16).contiguous()
+    out = torch.zeros((N, 2 * H, 2 * W, Cout), dtype=torch.float32, device=DEV)
+    ops.conv2d(x, wst, kh=2, kw=2, OH=H, OW=W, bias=b, out_f32=out, parities=4)
+    torch.cuda.synchronize()
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w, b, padding=1)
+    # the parity kernels are sums of up to four bf16-representable taps rounded to bf16 once more: operand rounding, as for
+    # every conv of the library
+    return rel_l2(out.permute(0, 3, 1, 2), ref), TOL_BF16
+
+
 # ------------------------------------------------------------------------------------------------ attention
 def case_attention(B=2, heads=8, d=40, Nq=1024, Nk=None, seed=20, fused_qkv=True, dtype=torch.bfloat16, causal=False):
     """``dtype`` fp16: the UNet's path (two exponentials per MUFU op, denominator from a ones column of V)."""
@@ -536,6 +557,11 @@ CASES = {
     "conv3x3_vae_cout512": lambda: case_conv(N=1, H=32, W=32, Cin=512, Cout=512, seed=24),
     "conv3x3_long_k_2chunk": lambda: case_conv(N=4, H=32, W=32, Cin=1280, Cout=640, bias_n=True, seed=25),
     "conv2x2_parity_strided_out": case_conv_strided_out,
+    # --- the four parity kernels in one launch (parities = 4): in-cluster split-K (8x8), one wave (16x16), two column chunks (32x32), batch 16
+    "upconv_one_launch_16x16": case_upsample_conv_one_launch,
+    "upconv_one_launch_8x8_splitk": lambda: case_upsample_conv_one_launch(N=2, H=8, W=8, seed=151),
+    "upconv_one_launch_32x32_c640": lambda: case_upsample_conv_one_launch(N=2, H=32, W=32, Cin=640, Cout=640, seed=152),
+    "upconv_one_launch_b16_ragged": lambda: case_upsample_conv_one_launch(N=16, H=7, W=9, Cin=320, Cout=320, seed=153),
     "conv3x3_unet8_splitk_b16": lambda: case_conv(N=16, H=8, W=8, Cin=1280, Cout=1280, bias_n=True, f32_out=True, seed=27),
     "conv3x3_unet8_splitk_shortcut": lambda: case_conv(N=16, H=8, W=8, Cin=1280, Cout=1280, x2c=2560, f32_out=True, seed=28),
     # --- deterministic split-K (epilogue_splitk): 8 / 4 / 3 / 2 slices, every epilogue flavour, ragged tiles
