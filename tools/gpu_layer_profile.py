@@ -28,7 +28,7 @@ if "nosplit" in sys.argv[3:]:
 if "nopdl" in sys.argv[3:]:
     _lib.load().rg_set_pdl(0)
 dev = torch.device("cuda", 0)
-pipe = StableDiffusionImg2ImgPipeline.from_random_init(seed=0).to(dev)
+pipe = StableDiffusionImg2ImgPipeline.from_random_init(seed=0, device="cuda").to(dev)
 out_lines = []
 
 
