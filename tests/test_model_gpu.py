@@ -121,6 +121,16 @@ def test_batched_call_equals_separate_calls():
         pipe(prompt=None, image=imgs, strength=0.5)          # diffusers' check_inputs behaviour
 
 
+def test_batch_invariance_is_bitwise_without_the_k_split():
+    """What the sharded sweep's bookkeeping contract rests on (sweep.run_sweep samples under ops.splitk(False)): with the K split
+    off, an image's uint8 result does not depend on the batch it was sampled in -- bit for bit, img2img and inpaint."""
+    import subprocess, sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "tools" / "gpu_batch_invariance.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "batch-invariant bit for bit: True" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
 def test_restoration_pipeline_drop_in():
     """The reference's outer API on the CUDA path: process() with random-init models, default prompts, result keys."""
     from PIL import Image
