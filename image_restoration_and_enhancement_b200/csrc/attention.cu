@@ -115,7 +115,7 @@ constexpr int kAttnThreads = 384;
 // Stagger (cycles) of query tile 1 behind tile 0 for the long key loops: the two warps that share an SM sub-partition
 // then run their exponential phase (MUFU-bound) and their bookkeeping (barrier round trips, tcgen05.ld / st, row max:
 // issue- and latency-bound, MUFU idle) in anti-phase instead of in lock-step.  About half a step period.
-constexpr int kAttnSkewCycles = 1300;
+constexpr int kAttnSkewCycles = 700;      // flat optimum 300..1100 cycles, lock-step again from ~1500 (profiles/r02_attn_variants.txt)
 #ifndef RG_ATTN_PSTREAM
 #define RG_ATTN_PSTREAM 1
 #endif
